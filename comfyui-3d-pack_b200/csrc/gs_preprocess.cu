@@ -1,0 +1,201 @@
+// Forward per-Gaussian preprocess: project + cull + EWA cov2D + extent + tile
+// rect + SH->RGB, fused into one pass that emits the 48 B splat record.
+//
+// Replaces preprocessCUDA of diff_gaussian_rasterization (called from
+// main_3DGS_renderer.py:927-936).  Algorithm per SURVEY.md App. A.1.1-4.
+//
+// THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: every value that decides
+// an integer output (cull, radius, rect, depth bits -> keys) is computed with the
+// exact IEEE fp32 operation order of oracle/gs_oracle.py::preprocess, so keys,
+// radii and tile lists are bit-exact against the oracle.  The kernel is HBM
+// bound (reads 4*(3+3+4+1+3M) B, writes 64 B per Gaussian), so losing FMA
+// contraction here costs nothing.
+#include "gs_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void sh_to_rgb(int deg, int M, const float* __restrict__ sh, float dx, float dy,
+                                          float dz, float& r, float& g, float& b) {
+    // sh: [M,3] of this Gaussian.  Basis as shared_utils/sh_utils.py:57-112.
+    float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    float x = dx * inv, y = dy * inv, z = dz * inv;
+    float bas[16];
+    bas[0] = SH_C0;
+    int nb = 1;
+    if (deg > 0) {
+        bas[1] = -SH_C1 * y; bas[2] = SH_C1 * z; bas[3] = -SH_C1 * x; nb = 4;
+        if (deg > 1) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            bas[4] = SH_C2_0 * xy; bas[5] = SH_C2_1 * yz; bas[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+            bas[7] = SH_C2_3 * xz; bas[8] = SH_C2_4 * (xx - yy); nb = 9;
+            if (deg > 2) {
+                bas[9] = SH_C3_0 * y * (3.0f * xx - yy);
+                bas[10] = SH_C3_1 * xy * z;
+                bas[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
+                bas[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                bas[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
+                bas[14] = SH_C3_5 * z * (xx - yy);
+                bas[15] = SH_C3_6 * x * (xx - 3.0f * yy);
+                nb = 16;
+            }
+        }
+    }
+    r = 0.f; g = 0.f; b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < nb) {
+            r += bas[k] * sh[3 * k + 0];
+            g += bas[k] * sh[3 * k + 1];
+            b += bas[k] * sh[3 * k + 2];
+        }
+    }
+    r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+}
+
+constexpr int PP_THREADS = 128;
+
+// One thread per Gaussian.  SH coefficients of the CTA's 128 Gaussians are one
+// contiguous span of global memory (128*M*12 B): it is staged into shared
+// memory with fully coalesced 128-bit loads, then each thread reads its own
+// row (row stride padded to an odd word count -> bank-conflict free).
+__global__ void __launch_bounds__(PP_THREADS)
+preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                  const float* __restrict__ colors_precomp, const float* __restrict__ opacities,
+                  const float* __restrict__ scales, const float* __restrict__ rotations,
+                  const float* __restrict__ cov3D_precomp, SplatRec* __restrict__ recs,
+                  int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids) {
+    extern __shared__ __align__(16) float s_sh[];
+    __shared__ float s_view[16], s_proj[16], s_cam[3];
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PP_THREADS;
+    if (tid < 16) { s_view[tid] = __ldg(va.view + tid); s_proj[tid] = __ldg(va.proj + tid); }
+    if (tid < 3) s_cam[tid] = __ldg(va.campos + tid);
+
+    const int row = 3 * M;
+    const int rowp = gs_rowp(row);
+    if (shs != nullptr)
+        gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
+    __syncthreads();
+
+    const int idx = base + tid;
+    if (idx >= N) return;
+    const float* m = s_view;
+    const float* p = s_proj;
+
+    const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const float tx = m[0] * x + m[4] * y + m[8] * z + m[12];
+    const float ty = m[1] * x + m[5] * y + m[9] * z + m[13];
+    const float tz = m[2] * x + m[6] * y + m[10] * z + m[14];
+
+    SplatRec rec;
+    rec.g = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec.k = make_float4(0.f, 0.f, 0.f, 0.f);
+    int my_radius = 0;
+    uint32_t tiles = 0;
+    uint32_t dkey = 0xFFFFFFFFu;
+
+    if (tz > 0.2f) {
+        const float hx = p[0] * x + p[4] * y + p[8] * z + p[12];
+        const float hy = p[1] * x + p[5] * y + p[9] * z + p[13];
+        const float hw = p[3] * x + p[7] * y + p[11] * z + p[15];
+        const float pw = 1.0f / (hw + 0.0000001f);
+        const float ndcx = hx * pw, ndcy = hy * pw;
+
+        float c0, c1, c2, c3, c4, c5;
+        if (cov3D_precomp != nullptr) {
+            const float* c = cov3D_precomp + 6 * (size_t)idx;
+            c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
+        } else {
+            const float mod = va.scale_modifier;
+            const float s0 = mod * scales[3 * idx + 0], s1 = mod * scales[3 * idx + 1], s2 = mod * scales[3 * idx + 2];
+            const float* q = rotations + 4 * (size_t)idx;
+            const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
+            const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz), R01 = 2.0f * (qx * qy - r * qz), R02 = 2.0f * (qx * qz + r * qy);
+            const float R10 = 2.0f * (qx * qy + r * qz), R11 = 1.0f - 2.0f * (qx * qx + qz * qz), R12 = 2.0f * (qy * qz - r * qx);
+            const float R20 = 2.0f * (qx * qz - r * qy), R21 = 2.0f * (qy * qz + r * qx), R22 = 1.0f - 2.0f * (qx * qx + qy * qy);
+            const float M00 = R00 * s0, M01 = R01 * s1, M02 = R02 * s2;
+            const float M10 = R10 * s0, M11 = R11 * s1, M12 = R12 * s2;
+            const float M20 = R20 * s0, M21 = R21 * s1, M22 = R22 * s2;
+            c0 = M00 * M00 + M01 * M01 + M02 * M02;
+            c1 = M00 * M10 + M01 * M11 + M02 * M12;
+            c2 = M00 * M20 + M01 * M21 + M02 * M22;
+            c3 = M10 * M10 + M11 * M11 + M12 * M12;
+            c4 = M10 * M20 + M11 * M21 + M12 * M22;
+            c5 = M20 * M20 + M21 * M21 + M22 * M22;
+        }
+
+        const float fx = va.focal_x, fy = va.focal_y;
+        const float limx = 1.3f * va.tanfovx, limy = 1.3f * va.tanfovy;
+        const float txtz = tx / tz, tytz = ty / tz;
+        const float cx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+        const float cy = fminf(limy, fmaxf(-limy, tytz)) * tz;
+        const float J00 = fx / tz, J02 = -(fx * cx) / (tz * tz);
+        const float J11 = fy / tz, J12 = -(fy * cy) / (tz * tz);
+        const float T00 = J00 * m[0] + J02 * m[2], T01 = J00 * m[4] + J02 * m[6], T02 = J00 * m[8] + J02 * m[10];
+        const float T10 = J11 * m[1] + J12 * m[2], T11 = J11 * m[5] + J12 * m[6], T12 = J11 * m[9] + J12 * m[10];
+        const float v00 = c0 * T00 + c1 * T01 + c2 * T02;
+        const float v01 = c1 * T00 + c3 * T01 + c4 * T02;
+        const float v02 = c2 * T00 + c4 * T01 + c5 * T02;
+        const float v10 = c0 * T10 + c1 * T11 + c2 * T12;
+        const float v11 = c1 * T10 + c3 * T11 + c4 * T12;
+        const float v12 = c2 * T10 + c4 * T11 + c5 * T12;
+        const float ca = T00 * v00 + T01 * v01 + T02 * v02 + 0.3f;
+        const float cb = T00 * v10 + T01 * v11 + T02 * v12;
+        const float cc = T10 * v10 + T11 * v11 + T12 * v12 + 0.3f;
+
+        const float det = ca * cc - cb * cb;
+        if (det != 0.0f) {
+            const float det_inv = 1.0f / det;
+            const float mid = 0.5f * (ca + cc);
+            const float disc = sqrtf(fmaxf(mid * mid - det, 0.1f));
+            const float lam1 = mid + disc, lam2 = mid - disc;
+            const float radf = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
+            const float px = ((ndcx + 1.0f) * (float)va.W - 1.0f) * 0.5f;
+            const float py = ((ndcy + 1.0f) * (float)va.H - 1.0f) * 0.5f;
+            int rad_i = (int)radf;
+            int x0, y0, x1, y1;
+            get_rect(px, py, rad_i, va.tiles_x, va.tiles_y, x0, y0, x1, y1);
+            const int area = (x1 - x0) * (y1 - y0);
+            if (area > 0) {
+                my_radius = rad_i;
+                tiles = (uint32_t)area;
+                dkey = __float_as_uint(tz);
+                float cr, cg, cbl;
+                if (colors_precomp != nullptr) {
+                    cr = colors_precomp[3 * idx + 0]; cg = colors_precomp[3 * idx + 1]; cbl = colors_precomp[3 * idx + 2];
+                } else {
+                    sh_to_rgb(va.sh_degree, M, s_sh + tid * rowp, x - s_cam[0], y - s_cam[1], z - s_cam[2], cr, cg, cbl);
+                }
+                rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
+                rec.c = make_float4(cc * det_inv, -cb * det_inv, ca * det_inv, opacities[idx]);
+                rec.k = make_float4(cr, cg, cbl, __uint_as_float(tiles));
+            }
+        }
+    }
+    recs[idx] = rec;
+    radii[idx] = my_radius;
+    tiles_touched[idx] = tiles;
+    depth_keys[idx] = dkey;
+    ids[idx] = (uint32_t)idx;
+}
+
+}  // namespace
+
+int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* opacities, const float* scales,
+                         const float* rotations, const float* cov3D_precomp, SplatRec* recs, int32_t* radii,
+                         uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, cudaStream_t s) {
+    if (N <= 0) return 0;
+    size_t smem = shs ? (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float) : 0;
+    if (smem > 48 * 1024) {
+        GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int blocks = (N + PP_THREADS - 1) / PP_THREADS;
+    preprocess_kernel<<<blocks, PP_THREADS, smem, s>>>(va, N, M, means3D, shs, colors_precomp, opacities, scales,
+                                                       rotations, cov3D_precomp, recs, radii, tiles_touched,
+                                                       depth_keys, ids);
+    GS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

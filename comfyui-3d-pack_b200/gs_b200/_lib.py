@@ -1,0 +1,73 @@
+"""ctypes binding of the C ABI declared in include/gs_b200.h.
+
+The CUDA library is the product; there is NO CPU fallback: importing this module
+raises if ``libgs_b200.so`` has not been built (``python __graft_entry__.py`` or
+``csrc/build.sh``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgs_b200.so")
+
+BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_SCRATCH = 0, 1, 2, 3
+
+
+class View(C.Structure):
+    _fields_ = [("image_height", C.c_int32), ("image_width", C.c_int32), ("tanfovx", C.c_float),
+                ("tanfovy", C.c_float), ("bg", C.c_void_p), ("scale_modifier", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("sh_degree", C.c_int32),
+                ("campos", C.c_void_p), ("prefiltered", C.c_int32), ("debug", C.c_int32)]
+
+
+class State(C.Structure):
+    _fields_ = [("geom", C.c_void_p), ("point_list", C.c_void_p), ("tile_keys", C.c_void_p),
+                ("ranges", C.c_void_p), ("n_contrib", C.c_void_p), ("final_T", C.c_void_p),
+                ("num_rendered", C.c_int64), ("num_gaussians", C.c_int32), ("tiles_x", C.c_int32),
+                ("tiles_y", C.c_int32), ("owned", C.c_void_p * 4)]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built. "
+        "Run `python __graft_entry__.py` (or comfyui-3d-pack_b200/csrc/build.sh). There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_P = C.c_void_p
+lib.gs_b200_abi_version.restype = C.c_int32
+lib.gs_b200_last_error.restype = C.c_char_p
+lib.gs_b200_rasterize_forward.restype = C.c_int32
+lib.gs_b200_rasterize_forward.argtypes = [C.POINTER(View), C.c_int32, C.c_int32] + [_P] * 7 + [_P] * 4 + \
+    [ALLOC_FN, _P, C.POINTER(State), _P]
+lib.gs_b200_rasterize_backward.restype = C.c_int32
+lib.gs_b200_rasterize_backward.argtypes = [C.POINTER(View), C.c_int32, C.c_int32] + [_P] * 7 + \
+    [_P, C.POINTER(State)] + [_P] * 3 + [_P] * 8 + [C.c_int32, ALLOC_FN, _P, _P]
+lib.gs_b200_state_free.restype = C.c_int32
+lib.gs_b200_state_free.argtypes = [C.POINTER(State), _P]
+lib.gs_b200_debug_sorted_keys.restype = C.c_int32
+lib.gs_b200_debug_sorted_keys.argtypes = [C.POINTER(State), _P, _P]
+lib.gs_b200_sort_scratch_bytes.restype = C.c_size_t
+lib.gs_b200_sort_scratch_bytes.argtypes = [C.c_int64]
+lib.gs_b200_sort_pairs_u32.restype = C.c_int32
+lib.gs_b200_sort_pairs_u32.argtypes = [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32), _P]
+lib.gs_b200_knn_mean_dist2.restype = C.c_int32
+lib.gs_b200_knn_mean_dist2.argtypes = [_P, C.c_int32, _P, _P]
+lib.gs_b200_step_host.restype = C.c_int32
+lib.gs_b200_step_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, C.c_int32, C.c_int32] + \
+    [_P] * 5 + [_P, _P, _P, C.POINTER(C.c_int64), _P]
+
+EXPORTS = ["gs_b200_abi_version", "gs_b200_last_error", "gs_b200_rasterize_forward", "gs_b200_rasterize_backward",
+           "gs_b200_state_free", "gs_b200_debug_sorted_keys", "gs_b200_sort_scratch_bytes",
+           "gs_b200_sort_pairs_u32", "gs_b200_knn_mean_dist2", "gs_b200_step_host"]
+
+
+def last_error() -> str:
+    return lib.gs_b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"gs_b200: {last_error()}")

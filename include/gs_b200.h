@@ -1,0 +1,158 @@
+/*
+ * gs_b200.h — C ABI of the B200-native 3D Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary for the path ComfyUI-3D-Pack reaches through the third-party
+ * Python package `diff_gaussian_rasterization` (ashawkey fork), whose two
+ * torch ops `rasterize_gaussians` / `rasterize_gaussians_backward` are what
+ *   MVs_Algorithms/GaussianSplatting/main_3DGS_renderer.py:840-936   (render)
+ *   MVs_Algorithms/GaussianSplatting/main_3DGS.py:205               (loss.backward)
+ *   Gen_3D_Modules/LGM/core/gs.py:57-84, TriplaneGaussian/models/renderer.py:209-304,
+ *   Gen_3D_Modules/TRELLIS/trellis/renderers/gaussian_render.py:62-137
+ * end up calling.  The reference binds that package by Python import name;
+ * this header is the C-level surface a binding (ctypes / pybind / cgo) links.
+ * Plain pointers and sizes only — no torch types.  All pointers are DEVICE
+ * pointers on the current CUDA device unless a function name ends in `_host`.
+ * Every function returns 0 on success, non-zero on error (message via
+ * gs_b200_last_error()).  Work is enqueued on `stream` (a cudaStream_t passed
+ * as void*; NULL = legacy default stream).
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_B200_ABI_VERSION 1
+#define GS_B200_TILE 16
+
+/* ---- view / settings ------------------------------------------------------
+ * Mirrors GaussianRasterizationSettings, the 12-field NamedTuple built at
+ * main_3DGS_renderer.py:849-862.  bg/viewmatrix/projmatrix/campos stay device
+ * pointers exactly as the reference passes CUDA tensors (no host sync).
+ *   viewmatrix = w2c^T   row-major 4x4   (camera_utils.py:205)
+ *   projmatrix = w2c^T @ P^T row-major    (camera_utils.py:213)
+ */
+typedef struct gs_b200_view {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float* bg;          /* [3]  */
+    float scale_modifier;
+    const float* viewmatrix;  /* [16] */
+    const float* projmatrix;  /* [16] */
+    int32_t sh_degree;
+    const float* campos;      /* [3]  */
+    int32_t prefiltered;      /* accepted, ignored (reference passes False) */
+    int32_t debug;            /* accepted; non-zero adds a stream sync + error check per stage */
+} gs_b200_view;
+
+/* ---- allocator callback ----------------------------------------------------
+ * Replaces the std::function<char*(size_t)> resize callbacks of the package's
+ * RasterizeGaussiansCUDA: the caller owns every buffer (SURVEY §8b ownership).
+ * tag says what the buffer is for; the callback returns >=256-byte aligned
+ * device memory valid on `stream`.  If `alloc` is NULL the library uses
+ * cudaMallocAsync on the stream and the caller releases saved state with
+ * gs_b200_state_free().
+ */
+enum { GS_B200_BUF_GEOM = 0, GS_B200_BUF_BINNING = 1, GS_B200_BUF_IMAGE = 2, GS_B200_BUF_SCRATCH = 3 };
+typedef void* (*gs_b200_alloc_fn)(void* user, int32_t tag, size_t bytes);
+
+/* ---- state kept between forward and backward -------------------------------
+ * (geomBuffer / binningBuffer / imgBuffer of the package.)  Filled by
+ * gs_b200_rasterize_forward; pointers live in buffers obtained through the
+ * callback, so freeing those buffers frees the state.
+ */
+typedef struct gs_b200_state {
+    void* geom;              /* N x 48 B splat records {px,py,depth,radius | conic a,b,c,opacity | r,g,b,tiles} */
+    uint32_t* point_list;    /* [P] Gaussian index per (tile,splat) pair, sorted by (tile, depth, index) */
+    uint32_t* tile_keys;     /* [P] tile id per sorted pair */
+    uint32_t* ranges;        /* [tiles][2] start,end into point_list */
+    uint32_t* n_contrib;     /* [H*W] 1-based position of the last blended splat */
+    float* final_T;          /* [H*W] transmittance after the last blended splat */
+    int64_t num_rendered;    /* P */
+    int32_t num_gaussians;   /* N */
+    int32_t tiles_x, tiles_y;
+    void* owned[4];          /* non-NULL only when the internal allocator was used */
+} gs_b200_state;
+
+int32_t gs_b200_abi_version(void);
+const char* gs_b200_last_error(void);
+
+/* Forward — replaces `_C.rasterize_gaussians` as called from
+ * GaussianRasterizer.forward (main_3DGS_renderer.py:927-936).
+ *   M        number of SH coefficients per channel in `shs` ([N,M,3]); ignored when colors_precomp != NULL
+ *   exactly one of shs / colors_precomp, exactly one of (scales,rotations) / cov3D_precomp
+ * Outputs (caller-allocated): out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W], radii[N] int32.
+ */
+int32_t gs_b200_rasterize_forward(
+    const gs_b200_view* view, int32_t N, int32_t M,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, const float* rotations, const float* cov3D_precomp,
+    float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+    gs_b200_alloc_fn alloc, void* alloc_user, gs_b200_state* state, void* stream);
+
+/* Backward — replaces `_C.rasterize_gaussians_backward` (triggered by
+ * loss.backward(), main_3DGS.py:205).  Gradient outputs are caller-allocated
+ * and OVERWRITTEN (accumulate==0) or ADDED TO (accumulate!=0; used by the
+ * multi-view optimisation step, which sums views in place):
+ *   dL_dmeans3D[N,3] dL_dmeans2D[N,3] (= NDC-space screen gradient, z=0; consumed at main_3DGS_renderer.py:767-769)
+ *   dL_dshs[N,M,3] | dL_dcolors[N,3]   dL_dopacities[N,1]
+ *   dL_dscales[N,3], dL_drotations[N,4] | dL_dcov3D[N,6]
+ * NULL gradient pointers for the unused alternative of each exclusive pair.
+ */
+int32_t gs_b200_rasterize_backward(
+    const gs_b200_view* view, int32_t N, int32_t M,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, const float* rotations, const float* cov3D_precomp,
+    const int32_t* radii, const gs_b200_state* state,
+    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+    float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dshs, float* dL_dcolors, float* dL_dopacities,
+    float* dL_dscales, float* dL_drotations, float* dL_dcov3D, int32_t accumulate,
+    gs_b200_alloc_fn alloc, void* alloc_user, void* stream);
+
+/* Release state buffers obtained with the internal allocator (alloc == NULL). */
+int32_t gs_b200_state_free(gs_b200_state* state, void* stream);
+
+/* Parity/debug: reconstruct the 64-bit sorted keys (tile<<32 | float_bits(depth))
+ * the package's binning stage would hold, for bit-exact comparison. keys_out[P]. */
+int32_t gs_b200_debug_sorted_keys(const gs_b200_state* state, uint64_t* keys_out, void* stream);
+
+/* CUB-free onesweep LSD radix sort of (u32 key, u32 value) pairs on bits
+ * [begin_bit,end_bit) — the replacement for cub::DeviceRadixSort::SortPairs in
+ * the package's binning stage.  keys/vals are ping-pong pairs of n elements;
+ * *result_in_alt receives 1 when the sorted data ended in keys_alt/vals_alt.
+ * scratch must hold gs_b200_sort_scratch_bytes(n) bytes. vals may be NULL (keys only). */
+size_t gs_b200_sort_scratch_bytes(int64_t n);
+int32_t gs_b200_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                               int64_t n, int32_t begin_bit, int32_t end_bit, void* scratch,
+                               int32_t* result_in_alt, void* stream);
+
+/* distCUDA2 replacement (simple_knn._C.distCUDA2, main_3DGS_renderer.py:408,419):
+ * mean squared distance to the 3 nearest neighbours. points[N,3] -> out[N]. */
+int32_t gs_b200_knn_mean_dist2(const float* points, int32_t N, float* out, void* stream);
+
+/* Multi-view optimisation step with HOST buffers (the e2e entry: H2D of the
+ * Gaussians, V x (forward + backward) with gradients summed over views on the
+ * device, D2H of the summed gradients).  Host pointers should be pinned.
+ *   views_host: V consecutive records of 40 floats:
+ *      [0..15] viewmatrix, [16..31] projmatrix, [32..34] campos, [35..37] bg, [38] tanfovx, [39] tanfovy
+ *   dL_dout_host: V x [5,H,W] (3 colour planes, depth, alpha) upstream gradients
+ *   grads_host:   [N,(3+3M+1+3+4)] packed per parameter group in the order
+ *                 means3D | shs | opacities | scales | rotations  (each contiguous), then means2D [N,3]
+ *   images_host:  optional V x [5,H,W] rendered (colour, depth, alpha); may be NULL
+ */
+int32_t gs_b200_step_host(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    int32_t N, int32_t M, const float* means3D_host, const float* shs_host, const float* opacities_host,
+    const float* scales_host, const float* rotations_host, const float* dL_dout_host,
+    float* grads_host, float* images_host, int64_t* num_rendered_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */
