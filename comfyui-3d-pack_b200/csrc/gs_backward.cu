@@ -266,6 +266,7 @@ int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float*
                                                                 scales, rotations, cov3D_precomp, radii, sg, dmeans3D,
                                                                 dmeans2D, dshs, dcolors, dopac, dscales, drots, dcov3D,
                                                                 accumulate);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

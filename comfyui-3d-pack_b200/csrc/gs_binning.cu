@@ -63,6 +63,7 @@ int gs_launch_emit(const SplatRec* recs, const uint32_t* sorted_ids, const uint3
                    int tiles_x, int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s) {
     if (N <= 0) return 0;
     emit_kernel<<<(N + 255) / 256, 256, 0, s>>>(recs, sorted_ids, offsets, N, tiles_x, tiles_y, tile_keys, vals);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -70,6 +71,7 @@ int gs_launch_emit(const SplatRec* recs, const uint32_t* sorted_ids, const uint3
 int gs_launch_ranges(const uint32_t* sorted_tile_keys, int64_t P, uint32_t* ranges, cudaStream_t s) {
     if (P <= 0) return 0;
     ranges_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(sorted_tile_keys, P, ranges);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -78,6 +80,7 @@ int gs_launch_sorted_keys(const SplatRec* recs, const uint32_t* point_list, cons
                           uint64_t* keys_out, cudaStream_t s) {
     if (P <= 0) return 0;
     sorted_keys_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(recs, point_list, tile_keys, P, keys_out);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -18,7 +18,34 @@ void gs_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+#include <atomic>
+#include <mutex>
+static std::atomic<long long> g_launches{0};
+void gs_count_launches(int n) { g_launches += n; }
+
 namespace {
+
+// ---- per-stage CUDA-event timing (off by default; bench.py turns it on for a profiling pass)
+struct StageEv { int stage; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<StageEv> g_prof;
+struct StageTimer {
+    cudaStream_t s; int idx = -1;
+    StageTimer(int stage, cudaStream_t s_) : s(s_) {
+        if (!g_prof_on) return;
+        std::lock_guard<std::mutex> l(g_prof_mu);
+        StageEv e; e.stage = stage;
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+        cudaEventRecord(e.a, s);
+        g_prof.push_back(e); idx = (int)g_prof.size() - 1;
+    }
+    ~StageTimer() {
+        if (idx < 0) return;
+        std::lock_guard<std::mutex> l(g_prof_mu);
+        if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].b, s);
+    }
+};
 
 struct Allocator {
     gs_b200_alloc_fn fn;
@@ -35,6 +62,17 @@ struct Allocator {
             p = fn(user, tag, bytes);
             if (!p) { failed = true; gs_set_error("allocator callback returned NULL for %zu bytes (tag %d)", bytes, tag); }
             return p;
+        }
+        static thread_local int pool_dev = -1;      // keep freed blocks in the pool across stream syncs
+        int devn = 0;
+        cudaGetDevice(&devn);
+        if (pool_dev != devn) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, devn) == cudaSuccess) {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            pool_dev = devn;
         }
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
         if (e != cudaSuccess) { failed = true; gs_set_error("cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(e)); return nullptr; }
@@ -114,6 +152,25 @@ unsigned long long* pinned_u64() {
 extern "C" {
 
 int32_t gs_b200_abi_version(void) { return GS_B200_ABI_VERSION; }
+int64_t gs_b200_launch_count(void) { return (int64_t)g_launches.load(); }
+void gs_b200_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    for (auto& e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+}
+int32_t gs_b200_profile_read(float* ms_out, int32_t* calls_out) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    for (int i = 0; i < GS_B200_NSTAGES; i++) { if (ms_out) ms_out[i] = 0.f; if (calls_out) calls_out[i] = 0; }
+    for (auto& e : g_prof) {
+        if (cudaEventSynchronize(e.b) != cudaSuccess) { gs_set_error("profile_read: event sync failed"); return 1; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) { gs_set_error("profile_read: elapsed failed"); return 1; }
+        if (ms_out) ms_out[e.stage] += ms;
+        if (calls_out) calls_out[e.stage] += 1;
+    }
+    return 0;
+}
 const char* gs_b200_last_error(void) { return g_err; }
 
 size_t gs_b200_sort_scratch_bytes(int64_t n) { return gs_sort_scratch_bytes(n); }
@@ -176,14 +233,17 @@ int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M
         void* sort_scratch = c.take<char>(sort_b);
         void* scan_scratch = c.take<char>(scan_b);
 
+        { StageTimer t(0, s);
         if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 recs, radii, tiles, dkeys, ids, s)) return 1;
+                                 recs, radii, tiles, dkeys, ids, s)) return 1; }
         STAGE_CHECK(dbg, s, "preprocess");
         int in_alt = 0;
-        if (gs_sort_pairs_u32(dkeys, dkeys_alt, ids, ids_alt, N, 0, 32, sort_scratch, &in_alt, s)) return 1;
+        { StageTimer t(1, s);
+        if (gs_sort_pairs_u32(dkeys, dkeys_alt, ids, ids_alt, N, 0, 32, sort_scratch, &in_alt, s)) return 1; }
         STAGE_CHECK(dbg, s, "depth sort");
         sorted_ids = in_alt ? ids_alt : ids;
-        if (gs_scan_gather_u32(tiles, sorted_ids, offsets, total, N, scan_scratch, s)) return 1;
+        { StageTimer t(2, s);
+        if (gs_scan_gather_u32(tiles, sorted_ids, offsets, total, N, scan_scratch, s)) return 1; }
         unsigned long long* hp = pinned_u64();
         if (!hp) { gs_set_error("cudaHostAlloc failed"); return 1; }
         GS_CUDA_CHECK(cudaMemcpyAsync(hp, total, 8, cudaMemcpyDeviceToHost, s));
@@ -213,16 +273,20 @@ int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M
         // start in the buffer that makes the last pass land in the saved (A) pair
         uint32_t *k0 = (npasses & 1) ? keys_b : state->tile_keys, *v0 = (npasses & 1) ? vals_b : state->point_list;
         uint32_t *k1 = (npasses & 1) ? state->tile_keys : keys_b, *v1 = (npasses & 1) ? state->point_list : vals_b;
-        if (gs_launch_emit(recs, sorted_ids, offsets, N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1;
+        { StageTimer t(3, s);
+        if (gs_launch_emit(recs, sorted_ids, offsets, N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1; }
         STAGE_CHECK(dbg, s, "emit");
         int in_alt = 0;
-        if (gs_sort_pairs_u32(k0, k1, v0, v1, (int64_t)P, 0, tbits, sort_scratch, &in_alt, s)) return 1;
+        { StageTimer t(4, s);
+        if (gs_sort_pairs_u32(k0, k1, v0, v1, (int64_t)P, 0, tbits, sort_scratch, &in_alt, s)) return 1; }
         STAGE_CHECK(dbg, s, "tile sort");
-        if (gs_launch_ranges(state->tile_keys, (int64_t)P, state->ranges, s)) return 1;
+        { StageTimer t(5, s);
+        if (gs_launch_ranges(state->tile_keys, (int64_t)P, state->ranges, s)) return 1; }
         STAGE_CHECK(dbg, s, "ranges");
     }
+    { StageTimer t(6, s);
     if (gs_launch_render_forward(va, recs, state->point_list, state->ranges, out_color, out_depth, out_alpha,
-                                 state->n_contrib, state->final_T, s)) return 1;
+                                 state->n_contrib, state->final_T, s)) return 1; }
     STAGE_CHECK(dbg, s, "render");
     return 0;
 }
@@ -252,13 +316,15 @@ int32_t gs_b200_rasterize_backward(const gs_b200_view* view, int32_t N, int32_t 
     if (A.failed) return 1;
     GS_CUDA_CHECK(cudaMemsetAsync(sg, 0, (size_t)N * sizeof(SplatGrad), s));
     if (state->num_rendered > 0) {
+        { StageTimer t(7, s);
         if (gs_launch_render_backward(va, (const SplatRec*)state->geom, state->point_list, state->ranges,
-                                      state->n_contrib, state->final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s)) return 1;
+                                      state->n_contrib, state->final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s)) return 1; }
         STAGE_CHECK(dbg, s, "render backward");
     }
+    { StageTimer t(8, s);
     if (gs_launch_preprocess_backward(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations,
                                       cov3D_precomp, radii, sg, dL_dmeans3D, dL_dmeans2D, dL_dshs, dL_dcolors,
-                                      dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s)) return 1;
+                                      dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, accumulate, s)) return 1; }
     STAGE_CHECK(dbg, s, "preprocess backward");
     return 0;
 }
@@ -293,14 +359,14 @@ struct HostStepCache {
 thread_local HostStepCache g_hs;
 }
 
-int32_t gs_b200_step_host(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+static int32_t step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
                           const float* views_host, int32_t N, int32_t M, const float* means3D_host,
                           const float* shs_host, const float* opacities_host, const float* scales_host,
-                          const float* rotations_host, const float* dL_dout_host, float* grads_host,
+                          const float* rotations_host, const float* dL_dout_host, float* grads_host, float* grads_dev,
                           float* images_host, int64_t* num_rendered_out, void* stream_) {
     cudaStream_t s = (cudaStream_t)stream_;
     if (V <= 0 || N <= 0 || !views_host || !means3D_host || !shs_host || !opacities_host || !scales_host ||
-        !rotations_host || !dL_dout_host || !grads_host) { gs_set_error("step_host: bad argument"); return 1; }
+        !rotations_host || !dL_dout_host || (!grads_host && !grads_dev)) { gs_set_error("step_host: bad argument"); return 1; }
     HostStepCache& C = g_hs;
     if (!C.copy_stream) {
         GS_CUDA_CHECK(cudaStreamCreateWithFlags(&C.copy_stream, cudaStreamNonBlocking));
@@ -389,11 +455,32 @@ int32_t gs_b200_step_host(int32_t V, int32_t H, int32_t W, int32_t sh_degree, fl
         gs_b200_state_free(&st, s);
         if (rc) return 1;
     }
-    GS_CUDA_CHECK(cudaMemcpyAsync(grads_host, d_grad, n_grad * 4, cudaMemcpyDeviceToHost, s));
+    if (grads_dev) GS_CUDA_CHECK(cudaMemcpyAsync(grads_dev, d_grad, n_grad * 4, cudaMemcpyDeviceToDevice, s));
+    if (grads_host) GS_CUDA_CHECK(cudaMemcpyAsync(grads_host, d_grad, n_grad * 4, cudaMemcpyDeviceToHost, s));
     GS_CUDA_CHECK(cudaStreamSynchronize(C.copy_stream));
-    GS_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (grads_host) GS_CUDA_CHECK(cudaStreamSynchronize(s));
     if (num_rendered_out) *num_rendered_out = rendered;
     return 0;
+}
+
+int32_t gs_b200_step_host(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                          const float* views_host, int32_t N, int32_t M, const float* means3D_host,
+                          const float* shs_host, const float* opacities_host, const float* scales_host,
+                          const float* rotations_host, const float* dL_dout_host, float* grads_host,
+                          float* images_host, int64_t* num_rendered_out, void* stream_) {
+    return step_host_impl(V, H, W, sh_degree, scale_modifier, views_host, N, M, means3D_host, shs_host,
+                          opacities_host, scales_host, rotations_host, dL_dout_host, grads_host, nullptr,
+                          images_host, num_rendered_out, stream_);
+}
+
+int32_t gs_b200_step_host_dev_grads(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                          const float* views_host, int32_t N, int32_t M, const float* means3D_host,
+                          const float* shs_host, const float* opacities_host, const float* scales_host,
+                          const float* rotations_host, const float* dL_dout_host, float* grads_dev,
+                          float* images_host, int64_t* num_rendered_out, void* stream_) {
+    return step_host_impl(V, H, W, sh_degree, scale_modifier, views_host, N, M, means3D_host, shs_host,
+                          opacities_host, scales_host, rotations_host, dL_dout_host, nullptr, grads_dev,
+                          images_host, num_rendered_out, stream_);
 }
 
 }  // extern "C"

@@ -130,6 +130,7 @@ __device__ __forceinline__ void gs_stage_rows_out(const float* __restrict__ s, f
     } while (0)
 
 void gs_set_error(const char* fmt, ...);
+void gs_count_launches(int n);     // instrumentation: kernels launched by this library
 
 // ---- launchers implemented in the .cu files --------------------------------
 int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,

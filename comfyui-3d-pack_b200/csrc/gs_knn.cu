@@ -52,6 +52,7 @@ int gs_launch_knn(const float* points, int N, float* out, cudaStream_t s) {
     if (N <= 0) return 0;
     if (!points || !out) { gs_set_error("knn: NULL"); return 1; }
     knn3_kernel<<<(N + KT - 1) / KT, KT, 0, s>>>(points, N, out);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -196,6 +196,7 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
     preprocess_kernel<<<blocks, PP_THREADS, smem, s>>>(va, N, M, means3D, shs, colors_precomp, opacities, scales,
                                                        rotations, cov3D_precomp, recs, radii, tiles_touched,
                                                        depth_keys, ids);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -271,6 +271,7 @@ int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uin
     dim3 grid(va.tiles_x, va.tiles_y);
     render_forward_kernel<<<grid, RB, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha,
                                               n_contrib, final_T);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -282,6 +283,7 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     dim3 grid(va.tiles_x, va.tiles_y);
     render_backward_kernel<<<grid, RB, 0, s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor,
                                                dL_ddepth, dL_dalpha, sg);
+    gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -335,6 +335,7 @@ int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32
         t = vin; vin = vout; vout = t;
         *result_in_alt ^= 1;
     }
+    gs_count_launches(2 + npasses);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -352,6 +353,7 @@ int gs_scan_gather_u32(const uint32_t* tiles, const uint32_t* ids, uint32_t* off
     scan_reduce<<<blocks, SC_THREADS, 0, s>>>(tiles, ids, n, bs);
     scan_block_sums<<<1, 1024, 0, s>>>(bs, blocks, total);
     scan_apply<<<blocks, SC_THREADS, 0, s>>>(tiles, ids, n, bs, offsets);
+    gs_count_launches(3);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

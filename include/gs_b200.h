@@ -151,6 +151,24 @@ int32_t gs_b200_step_host(
     int32_t N, int32_t M, const float* means3D_host, const float* shs_host, const float* opacities_host,
     const float* scales_host, const float* rotations_host, const float* dL_dout_host,
     float* grads_host, float* images_host, int64_t* num_rendered_out, void* stream);
+/* Same step, but the summed gradients are left on the device: copied (D2D) into
+ * grads_dev[N*(11+3M)+3N] instead of going to the host, so a multi-GPU caller can
+ * all-reduce them before its own D2H.  grads_host may then be NULL. */
+int32_t gs_b200_step_host_dev_grads(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    int32_t N, int32_t M, const float* means3D_host, const float* shs_host, const float* opacities_host,
+    const float* scales_host, const float* rotations_host, const float* dL_dout_host,
+    float* grads_dev, float* images_host, int64_t* num_rendered_out, void* stream);
+
+/* ---- instrumentation (bench.py): kernel-launch counter and per-stage CUDA-event timing ------
+ * Stages: 0 preprocess, 1 depth sort, 2 scan, 3 emit, 4 tile sort, 5 ranges, 6 composite fwd,
+ *         7 composite bwd, 8 preprocess bwd.  Events are recorded on the stream each stage is
+ * launched on; gs_b200_profile_read synchronises those events and returns accumulated
+ * milliseconds and call counts since the last gs_b200_profile_enable(1). */
+#define GS_B200_NSTAGES 9
+int64_t gs_b200_launch_count(void);
+void gs_b200_profile_enable(int32_t on);
+int32_t gs_b200_profile_read(float* ms_out, int32_t* calls_out);
 
 #ifdef __cplusplus
 }
