@@ -179,7 +179,7 @@ def run_b200(args):
     dl = dl_cpu.to(dev)
 
     def step():
-        pairs = optim_step.step_device(params, views, dl)
+        pairs = optim_step.step_device_pipelined(params, views, dl)
         if world > 1:
             dist.all_reduce(params.grads)
         return pairs

@@ -67,13 +67,8 @@ preprocess_backward_kernel(ViewArgs va, int N, int M, const float* __restrict__ 
         const float pw = 1.0f / (hw + 0.0000001f);
 
         // ---- 2-D mean (pixel -> NDC -> world) and depth ---------------------
-        g2x = gg.x * (0.5f * (float)va.W);
-        g2y = gg.y * (0.5f * (float)va.H);
-        const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
-        dmx = (p[0] * pw - p[3] * mul1) * g2x + (p[1] * pw - p[3] * mul2) * g2y;
-        dmy = (p[4] * pw - p[7] * mul1) * g2x + (p[5] * pw - p[7] * mul2) * g2y;
-        dmz = (p[8] * pw - p[11] * mul1) * g2x + (p[9] * pw - p[11] * mul2) * g2y;
-        dmx += m[2] * gg.z; dmy += m[6] * gg.z; dmz += m[10] * gg.z;
+        // (filled in after the conic is recomputed below: dL/dpx = -(A*Swx + B*Swy), dL/dpy = -(B*Swx + C*Swy))
+        dmx = m[2] * gg.z; dmy = m[6] * gg.z; dmz = m[10] * gg.z;
         dop = gc4.w;
 
         // ---- colour ---------------------------------------------------------
@@ -173,7 +168,19 @@ preprocess_backward_kernel(ViewArgs va, int N, int M, const float* __restrict__ 
         const float cc = T10 * v10 + T11 * v11 + T12 * v12 + 0.3f;
         const float denom = ca * cc - cb * cb;
         const float d2i = 1.0f / (denom * denom + 0.0000001f);
-        const float gA = gc4.x, gB = gc4.y, gC = gc4.z;       // true partials wrt conic a,b,c
+        // composite hands over raw moment sums; true partials wrt the conic (A,B,C) and the pixel mean:
+        const float gA = -0.5f * gc4.x, gB = -gc4.y, gC = -0.5f * gc4.z;
+        {
+            const float di = (denom != 0.f) ? 1.0f / denom : 0.f;
+            const float cA = cc * di, cB = -cb * di, cC = ca * di;
+            const float dpx = -(cA * gg.x + cB * gg.y), dpy = -(cB * gg.x + cC * gg.y);
+            g2x = dpx * (0.5f * (float)va.W);
+            g2y = dpy * (0.5f * (float)va.H);
+            const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
+            dmx += (p[0] * pw - p[3] * mul1) * g2x + (p[1] * pw - p[3] * mul2) * g2y;
+            dmy += (p[4] * pw - p[7] * mul1) * g2x + (p[5] * pw - p[7] * mul2) * g2y;
+            dmz += (p[8] * pw - p[11] * mul1) * g2x + (p[9] * pw - p[11] * mul2) * g2y;
+        }
         float ga = 0.f, gb = 0.f, gcc = 0.f;
         if (denom != 0.f) {
             ga = d2i * (-cc * cc * gA + cb * cc * gB - cb * cb * gC);

@@ -184,24 +184,38 @@ int32_t gs_b200_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* val
     return rc;
 }
 
-int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
-                                  const float* shs, const float* colors_precomp, const float* opacities,
-                                  const float* scales, const float* rotations, const float* cov3D_precomp,
-                                  float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
-                                  gs_b200_alloc_fn alloc, void* alloc_user, gs_b200_state* state, void* stream_) {
-    cudaStream_t s = (cudaStream_t)stream_;
-    ViewArgs va;
-    if (make_view_args(view, va)) return 1;
+// ---- forward, split at the one host round-trip (number of (tile,splat) pairs) -----------------
+// Phase A: preprocess -> depth sort -> gather-scan -> async D2H of the pair count.
+// Phase B (needs P on the host to size the binning buffers): emit -> tile sort -> ranges -> composite.
+struct FwdCtx {
+    ViewArgs va; int N = 0, M = 0, dbg = 0;
+    Allocator A;
+    gs_b200_state* state = nullptr;
+    SplatRec* recs = nullptr;
+    uint32_t *sorted_ids = nullptr, *offsets = nullptr;
+    unsigned long long* host_total = nullptr;      // pinned
+    float *out_color = nullptr, *out_depth = nullptr, *out_alpha = nullptr;
+    cudaStream_t s = nullptr;
+    FwdCtx(gs_b200_alloc_fn fn, void* user, cudaStream_t st) : A{fn, user, st}, s(st) {}
+};
+
+static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
+                       const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                       const float* rotations, const float* cov3D_precomp, float* out_color, float* out_depth,
+                       float* out_alpha, int32_t* radii, gs_b200_state* state, unsigned long long* host_total) {
+    cudaStream_t s = c.s;
+    if (make_view_args(view, c.va)) return 1;
     if (check_inputs(N, M, view->sh_degree, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)) return 1;
     if (!out_color || !out_depth || !out_alpha || (N > 0 && !radii) || !state) { gs_set_error("forward: NULL output"); return 1; }
-    const int dbg = view->debug;
+    const ViewArgs& va = c.va;
+    c.N = N; c.M = M; c.dbg = view->debug; c.state = state; c.host_total = host_total;
+    c.out_color = out_color; c.out_depth = out_depth; c.out_alpha = out_alpha;
     memset(state, 0, sizeof(*state));
     state->num_gaussians = N; state->tiles_x = va.tiles_x; state->tiles_y = va.tiles_y;
-    Allocator A{alloc, alloc_user, s};
+    Allocator& A = c.A;
     const size_t npix = (size_t)va.W * va.H;
     const int ntiles = va.tiles_x * va.tiles_y;
 
-    // ---- image state -----------------------------------------------------------
     const size_t img_bytes = Carver::need((size_t)ntiles * 2, 4) + Carver::need(npix, 4) * 2;
     void* img = A.get(GS_B200_BUF_IMAGE, img_bytes, &state->owned[GS_B200_BUF_IMAGE]);
     if (A.failed) return 1;
@@ -211,49 +225,51 @@ int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M
     state->final_T = ci.take<float>(npix);
     GS_CUDA_CHECK(cudaMemsetAsync(state->ranges, 0, (size_t)ntiles * 2 * 4, s));
 
-    // ---- per-Gaussian stage ------------------------------------------------------
-    SplatRec* recs = (SplatRec*)A.get(GS_B200_BUF_GEOM, (size_t)N * sizeof(SplatRec), &state->owned[GS_B200_BUF_GEOM]);
+    c.recs = (SplatRec*)A.get(GS_B200_BUF_GEOM, (size_t)N * sizeof(SplatRec), &state->owned[GS_B200_BUF_GEOM]);
     if (A.failed) return 1;
-    state->geom = recs;
-    unsigned long long P = 0;
-    uint32_t *sorted_ids = nullptr, *offsets = nullptr;
+    state->geom = c.recs;
+    *host_total = 0;
     if (N > 0) {
         const size_t sort_b = gs_sort_scratch_bytes(N), scan_b = gs_scan_scratch_bytes(N);
         const size_t sc_bytes = Carver::need(N, 4) * 6 + Carver::need(1, 8) + Carver::need(sort_b, 1) + Carver::need(scan_b, 1);
         void* sc = A.get(GS_B200_BUF_SCRATCH, sc_bytes);
         if (A.failed) return 1;
-        Carver c(sc);
-        uint32_t* tiles = c.take<uint32_t>(N);
-        uint32_t* dkeys = c.take<uint32_t>(N);
-        uint32_t* ids = c.take<uint32_t>(N);
-        uint32_t* dkeys_alt = c.take<uint32_t>(N);
-        uint32_t* ids_alt = c.take<uint32_t>(N);
-        offsets = c.take<uint32_t>(N);
-        unsigned long long* total = c.take<unsigned long long>(1);
-        void* sort_scratch = c.take<char>(sort_b);
-        void* scan_scratch = c.take<char>(scan_b);
-
+        Carver cv(sc);
+        uint32_t* tiles = cv.take<uint32_t>(N);
+        uint32_t* dkeys = cv.take<uint32_t>(N);
+        uint32_t* ids = cv.take<uint32_t>(N);
+        uint32_t* dkeys_alt = cv.take<uint32_t>(N);
+        uint32_t* ids_alt = cv.take<uint32_t>(N);
+        c.offsets = cv.take<uint32_t>(N);
+        unsigned long long* total = cv.take<unsigned long long>(1);
+        void* sort_scratch = cv.take<char>(sort_b);
+        void* scan_scratch = cv.take<char>(scan_b);
         { StageTimer t(0, s);
         if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 recs, radii, tiles, dkeys, ids, s)) return 1; }
-        STAGE_CHECK(dbg, s, "preprocess");
+                                 c.recs, radii, tiles, dkeys, ids, s)) return 1; }
+        STAGE_CHECK(c.dbg, s, "preprocess");
         int in_alt = 0;
         { StageTimer t(1, s);
         if (gs_sort_pairs_u32(dkeys, dkeys_alt, ids, ids_alt, N, 0, 32, sort_scratch, &in_alt, s)) return 1; }
-        STAGE_CHECK(dbg, s, "depth sort");
-        sorted_ids = in_alt ? ids_alt : ids;
+        STAGE_CHECK(c.dbg, s, "depth sort");
+        c.sorted_ids = in_alt ? ids_alt : ids;
         { StageTimer t(2, s);
-        if (gs_scan_gather_u32(tiles, sorted_ids, offsets, total, N, scan_scratch, s)) return 1; }
-        unsigned long long* hp = pinned_u64();
-        if (!hp) { gs_set_error("cudaHostAlloc failed"); return 1; }
-        GS_CUDA_CHECK(cudaMemcpyAsync(hp, total, 8, cudaMemcpyDeviceToHost, s));
-        GS_CUDA_CHECK(cudaStreamSynchronize(s));
-        P = *hp;
+        if (gs_scan_gather_u32(tiles, c.sorted_ids, c.offsets, total, N, scan_scratch, s)) return 1; }
+        GS_CUDA_CHECK(cudaMemcpyAsync(host_total, total, 8, cudaMemcpyDeviceToHost, s));
     }
+    return 0;
+}
+
+// caller has made sure the D2H of phase A completed (stream or event sync)
+static int fwd_phase_b(FwdCtx& c) {
+    cudaStream_t s = c.s;
+    const ViewArgs& va = c.va;
+    gs_b200_state* state = c.state;
+    Allocator& A = c.A;
+    const unsigned long long P = *c.host_total;
+    const int ntiles = va.tiles_x * va.tiles_y;
     if (P >= (1ull << 30)) { gs_set_error("too many (tile,splat) pairs: %llu", P); return 1; }
     state->num_rendered = (int64_t)P;
-
-    // ---- binning -----------------------------------------------------------------
     const size_t bin_bytes = Carver::need(P, 4) * 2;
     void* bin = A.get(GS_B200_BUF_BINNING, bin_bytes, &state->owned[GS_B200_BUF_BINNING]);
     if (A.failed) return 1;
@@ -270,25 +286,40 @@ int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M
         void* sort_scratch = c2.take<char>(sort_b);
         const int tbits = bits_for(ntiles);
         const int npasses = (tbits + 7) / 8;
-        // start in the buffer that makes the last pass land in the saved (A) pair
+        // start in the buffer that makes the last pass land in the saved pair
         uint32_t *k0 = (npasses & 1) ? keys_b : state->tile_keys, *v0 = (npasses & 1) ? vals_b : state->point_list;
         uint32_t *k1 = (npasses & 1) ? state->tile_keys : keys_b, *v1 = (npasses & 1) ? state->point_list : vals_b;
         { StageTimer t(3, s);
-        if (gs_launch_emit(recs, sorted_ids, offsets, N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1; }
-        STAGE_CHECK(dbg, s, "emit");
+        if (gs_launch_emit(c.recs, c.sorted_ids, c.offsets, c.N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1; }
+        STAGE_CHECK(c.dbg, s, "emit");
         int in_alt = 0;
         { StageTimer t(4, s);
         if (gs_sort_pairs_u32(k0, k1, v0, v1, (int64_t)P, 0, tbits, sort_scratch, &in_alt, s)) return 1; }
-        STAGE_CHECK(dbg, s, "tile sort");
+        STAGE_CHECK(c.dbg, s, "tile sort");
         { StageTimer t(5, s);
         if (gs_launch_ranges(state->tile_keys, (int64_t)P, state->ranges, s)) return 1; }
-        STAGE_CHECK(dbg, s, "ranges");
+        STAGE_CHECK(c.dbg, s, "ranges");
     }
     { StageTimer t(6, s);
-    if (gs_launch_render_forward(va, recs, state->point_list, state->ranges, out_color, out_depth, out_alpha,
+    if (gs_launch_render_forward(va, c.recs, state->point_list, state->ranges, c.out_color, c.out_depth, c.out_alpha,
                                  state->n_contrib, state->final_T, s)) return 1; }
-    STAGE_CHECK(dbg, s, "render");
+    STAGE_CHECK(c.dbg, s, "render");
     return 0;
+}
+
+int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
+                                  const float* shs, const float* colors_precomp, const float* opacities,
+                                  const float* scales, const float* rotations, const float* cov3D_precomp,
+                                  float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                                  gs_b200_alloc_fn alloc, void* alloc_user, gs_b200_state* state, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    unsigned long long* hp = pinned_u64();
+    if (!hp) { gs_set_error("cudaHostAlloc failed"); return 1; }
+    FwdCtx c(alloc, alloc_user, s);
+    if (fwd_phase_a(c, view, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                    out_color, out_depth, out_alpha, radii, state, hp)) return 1;
+    GS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return fwd_phase_b(c);
 }
 
 int32_t gs_b200_rasterize_backward(const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
@@ -347,120 +378,237 @@ int32_t gs_b200_knn_mean_dist2(const float* points, int32_t N, float* out, void*
 }
 
 // ---------------------------------------------------------------------------------
-// Multi-view optimisation step with host buffers (e2e entry).
+// Multi-view optimisation step (device-resident or host buffers).
+//
+// Views are software-pipelined over TWO internal streams with per-slot grow-only
+// workspaces (no allocation in steady state): while view v's composite kernels
+// (instruction-issue bound) run on one stream, view v+1's preprocess / sorts
+// (memory bound) run on the other, and the host's wait for v+1's pair count is
+// hidden behind the GPU work already queued for v.
 // ---------------------------------------------------------------------------------
 namespace {
-struct HostStepCache {
-    void* dev = nullptr; size_t bytes = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t up_done[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, img_ready[2] = {nullptr, nullptr},
-                img_copied[2] = {nullptr, nullptr};
+
+struct Region { void* p = nullptr; size_t cap = 0; };
+struct Slot {
+    cudaStream_t stream = nullptr;
+    Region saved[3];                 // GEOM, BINNING, IMAGE
+    Region arena; size_t arena_off = 0, arena_want = 0;
+    std::vector<void*> overflow;
+    Region sgrad, radii, image;
+    unsigned long long* host_total = nullptr;
+    cudaEvent_t evA = nullptr, evDone = nullptr;
+    bool failed = false;
+
+    static int ensure(Region& r, size_t bytes, cudaStream_t st) {
+        if (r.cap >= bytes) return 0;
+        if (r.p) { cudaStreamSynchronize(st); cudaFree(r.p); r.p = nullptr; r.cap = 0; }
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMalloc(&r.p, want) != cudaSuccess) { gs_set_error("cudaMalloc(%zu) failed", want); return 1; }
+        r.cap = want;
+        return 0;
+    }
+    void begin_call() {
+        // grow the arena to what the previous call needed in total (so overflow is a warm-up-only path)
+        if (arena_want > arena.cap) { release_overflow(); ensure(arena, arena_want, stream); }
+        arena_off = 0; arena_want = 0;
+    }
+    void release_overflow() {
+        if (overflow.empty()) return;
+        cudaStreamSynchronize(stream);
+        for (void* p : overflow) cudaFree(p);
+        overflow.clear();
+    }
+    void* alloc(int tag, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (tag != GS_B200_BUF_SCRATCH) {
+            if (ensure(saved[tag], bytes, stream)) { failed = true; return nullptr; }
+            return saved[tag].p;
+        }
+        arena_want += bytes;
+        if (arena_off + bytes <= arena.cap) { void* p = (char*)arena.p + arena_off; arena_off += bytes; return p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { failed = true; gs_set_error("cudaMalloc(%zu) failed", bytes); return nullptr; }
+        overflow.push_back(p);
+        return p;
+    }
 };
-thread_local HostStepCache g_hs;
+void* slot_alloc_cb(void* user, int32_t tag, size_t bytes) { return ((Slot*)user)->alloc(tag, bytes); }
+
+struct StepCache {
+    Slot slot[2];
+    bool init = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t evFork = nullptr, evPB = nullptr;
+    std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
+    Region host_stage;                           // device copies of host inputs (step_host)
+    int ensure_init() {
+        if (init) return 0;
+        for (int i = 0; i < 2; i++) {
+            GS_CUDA_CHECK(cudaStreamCreateWithFlags(&slot[i].stream, cudaStreamNonBlocking));
+            GS_CUDA_CHECK(cudaEventCreateWithFlags(&slot[i].evA, cudaEventDisableTiming));
+            GS_CUDA_CHECK(cudaEventCreateWithFlags(&slot[i].evDone, cudaEventDisableTiming));
+            GS_CUDA_CHECK(cudaHostAlloc((void**)&slot[i].host_total, 64, cudaHostAllocDefault));
+        }
+        GS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evPB, cudaEventDisableTiming));
+        init = true;
+        return 0;
+    }
+};
+thread_local StepCache g_step;
+
+struct PackedPtrs { float *means, *shs, *opac, *scales, *rots, *m2d; };
+PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
+    PackedPtrs p;
+    p.means = base; p.shs = p.means + N * 3; p.opac = p.shs + N * 3 * M; p.scales = p.opac + N;
+    p.rots = p.scales + N * 3; p.m2d = with_m2d ? p.rots + N * 4 : nullptr;
+    return p;
 }
 
-static int32_t step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
-                          const float* views_host, int32_t N, int32_t M, const float* means3D_host,
-                          const float* shs_host, const float* opacities_host, const float* scales_host,
-                          const float* rotations_host, const float* dL_dout_host, float* grads_host, float* grads_dev,
-                          float* images_host, int64_t* num_rendered_out, void* stream_) {
+// Device-resident core.  views_host gives tanfov per view (host side), views_dev the matrices.
+int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const float* views_host,
+              const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
+              const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
+              cudaStream_t user) {
+    StepCache& C = g_step;
+    if (C.ensure_init()) return 1;
+    const size_t npix = (size_t)H * W;
+    // fork: both slot streams start after everything already queued on the caller's stream
+    GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
+    for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evFork, 0));
+
+    gs_b200_state st[2];
+    gs_b200_view view[2];
+    FwdCtx* ctx[2] = {nullptr, nullptr};
+    int64_t rendered = 0;
+    int rc = 0;
+
+    auto launch_a = [&](int v) -> int {
+        Slot& S = C.slot[v & 1];
+        S.begin_call();
+        if (Slot::ensure(S.radii, (size_t)N * 4, S.stream) || Slot::ensure(S.sgrad, (size_t)N * sizeof(SplatGrad), S.stream) ||
+            (!images_dev && Slot::ensure(S.image, 5 * npix * 4, S.stream))) return 1;
+        const float* vh = views_host + (size_t)v * 40;
+        const float* vd = views_dev + (size_t)v * 40;
+        gs_b200_view& vw = view[v & 1];
+        vw.image_height = H; vw.image_width = W; vw.tanfovx = vh[38]; vw.tanfovy = vh[39];
+        vw.bg = vd + 35; vw.scale_modifier = scale_modifier; vw.viewmatrix = vd; vw.projmatrix = vd + 16;
+        vw.sh_degree = sh_degree; vw.campos = vd + 32; vw.prefiltered = 0; vw.debug = 0;
+        float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
+        delete ctx[v & 1];
+        ctx[v & 1] = new FwdCtx(slot_alloc_cb, &S, S.stream);
+        if (fwd_phase_a(*ctx[v & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
+                        img, img + 3 * npix, img + 4 * npix, (int32_t*)S.radii.p, &st[v & 1], S.host_total)) return 1;
+        GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
+        return S.failed ? 1 : 0;
+    };
+
+    rc = launch_a(0);
+    for (int v = 0; v < V && !rc; v++) {
+        Slot& S = C.slot[v & 1];
+        if (v + 1 < V) { rc = launch_a(v + 1); if (rc) break; }
+        GS_CUDA_CHECK(cudaEventSynchronize(S.evA));
+        if ((rc = fwd_phase_b(*ctx[v & 1]))) break;
+        rendered += st[v & 1].num_rendered;
+        // ---- backward of view v on the same stream
+        SplatGrad* sg = (SplatGrad*)S.sgrad.p;
+        GS_CUDA_CHECK(cudaMemsetAsync(sg, 0, (size_t)N * sizeof(SplatGrad), S.stream));
+        const float* up = dL_dout_dev + (size_t)v * 5 * npix;
+        if (up_ready) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, up_ready[v], 0));
+        if (st[v & 1].num_rendered > 0) {
+            StageTimer t(7, S.stream);
+            if ((rc = gs_launch_render_backward(ctx[v & 1]->va, (const SplatRec*)st[v & 1].geom, st[v & 1].point_list,
+                                                st[v & 1].ranges, st[v & 1].n_contrib, st[v & 1].final_T, up,
+                                                up + 3 * npix, up + 4 * npix, sg, S.stream))) break;
+        }
+        // gradient accumulation into the shared packed buffer is ordered view by view
+        if (v > 0) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, C.evPB, 0));
+        {
+            StageTimer t(8, S.stream);
+            if ((rc = gs_launch_preprocess_backward(ctx[v & 1]->va, N, M, par.means, par.shs, nullptr, par.opac, par.scales,
+                                                    par.rots, nullptr, (const int32_t*)S.radii.p, sg, grd.means, grd.m2d,
+                                                    grd.shs, nullptr, grd.opac, grd.scales, grd.rots, nullptr, 1, S.stream))) break;
+        }
+        GS_CUDA_CHECK(cudaEventRecord(C.evPB, S.stream));
+        if (S.failed) { rc = 1; break; }
+    }
+    for (int i = 0; i < 2; i++) { delete ctx[i]; ctx[i] = nullptr; }
+    // join: the caller's stream continues after both slot streams
+    for (int i = 0; i < 2; i++) {
+        cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
+        cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
+    }
+    if (num_rendered_out) *num_rendered_out = rendered;
+    return rc;
+}
+
+int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                   const float* views_host, int32_t N, int32_t M, const float* means3D_host,
+                   const float* shs_host, const float* opacities_host, const float* scales_host,
+                   const float* rotations_host, const float* dL_dout_host, float* grads_host, float* grads_dev,
+                   float* images_host, int64_t* num_rendered_out, void* stream_) {
     cudaStream_t s = (cudaStream_t)stream_;
     if (V <= 0 || N <= 0 || !views_host || !means3D_host || !shs_host || !opacities_host || !scales_host ||
         !rotations_host || !dL_dout_host || (!grads_host && !grads_dev)) { gs_set_error("step_host: bad argument"); return 1; }
-    HostStepCache& C = g_hs;
-    if (!C.copy_stream) {
-        GS_CUDA_CHECK(cudaStreamCreateWithFlags(&C.copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            GS_CUDA_CHECK(cudaEventCreateWithFlags(&C.up_done[i], cudaEventDisableTiming));
-            GS_CUDA_CHECK(cudaEventCreateWithFlags(&C.consumed[i], cudaEventDisableTiming));
-            GS_CUDA_CHECK(cudaEventCreateWithFlags(&C.img_ready[i], cudaEventDisableTiming));
-            GS_CUDA_CHECK(cudaEventCreateWithFlags(&C.img_copied[i], cudaEventDisableTiming));
-        }
-    }
+    StepCache& C = g_step;
+    if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
     const size_t n_par = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4);
     const size_t n_grad = n_par + (size_t)N * 3;
     const size_t need = Carver::need(n_par, 4) + Carver::need(n_grad, 4) + Carver::need((size_t)V * 40, 4) +
-                        Carver::need(5 * npix, 4) * 4 + Carver::need(N, 4);
-    if (C.bytes < need) {
-        if (C.dev) cudaFree(C.dev);
-        GS_CUDA_CHECK(cudaMalloc(&C.dev, need));
-        C.bytes = need;
-    }
-    Carver c(C.dev);
+                        Carver::need((size_t)V * 5 * npix, 4) * (images_host ? 2 : 1);
+    if (Slot::ensure(C.host_stage, need, s)) return 1;
+    Carver c(C.host_stage.p);
     float* d_par = c.take<float>(n_par);
     float* d_grad = c.take<float>(n_grad);
     float* d_views = c.take<float>((size_t)V * 40);
-    float* d_up[2] = {c.take<float>(5 * npix), c.take<float>(5 * npix)};
-    float* d_img[2] = {c.take<float>(5 * npix), c.take<float>(5 * npix)};
-    int32_t* d_radii = c.take<int32_t>(N);
-
-    float* d_means = d_par;
-    float* d_shs = d_means + (size_t)N * 3;
-    float* d_opac = d_shs + (size_t)N * 3 * M;
-    float* d_scales = d_opac + N;
-    float* d_rots = d_scales + (size_t)N * 3;
-    float* g_means = d_grad;
-    float* g_shs = g_means + (size_t)N * 3;
-    float* g_opac = g_shs + (size_t)N * 3 * M;
-    float* g_scales = g_opac + N;
-    float* g_rots = g_scales + (size_t)N * 3;
-    float* g_m2d = g_rots + (size_t)N * 4;
-
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_means, means3D_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_shs, shs_host, (size_t)N * 12 * M, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_opac, opacities_host, (size_t)N * 4, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_scales, scales_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_rots, rotations_host, (size_t)N * 16, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_views, views_host, (size_t)V * 160, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemsetAsync(d_grad, 0, n_grad * 4, s));
-
-    // upstream-gradient uploads run ahead on the copy stream (double buffered)
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_up[0], dL_dout_host, 5 * npix * 4, cudaMemcpyHostToDevice, C.copy_stream));
-    GS_CUDA_CHECK(cudaEventRecord(C.up_done[0], C.copy_stream));
-    int64_t rendered = 0;
-    for (int v = 0; v < V; v++) {
-        const int b = v & 1;
-        if (v + 1 < V) {
-            const int nb = (v + 1) & 1;
-            if (v >= 1) GS_CUDA_CHECK(cudaStreamWaitEvent(C.copy_stream, C.consumed[nb], 0));
-            GS_CUDA_CHECK(cudaMemcpyAsync(d_up[nb], dL_dout_host + (size_t)(v + 1) * 5 * npix, 5 * npix * 4,
-                                          cudaMemcpyHostToDevice, C.copy_stream));
-            GS_CUDA_CHECK(cudaEventRecord(C.up_done[nb], C.copy_stream));
-        }
-        const float* vh = views_host + (size_t)v * 40;
-        const float* vd = d_views + (size_t)v * 40;
-        gs_b200_view view;
-        view.image_height = H; view.image_width = W; view.tanfovx = vh[38]; view.tanfovy = vh[39];
-        view.bg = vd + 35; view.scale_modifier = scale_modifier; view.viewmatrix = vd; view.projmatrix = vd + 16;
-        view.sh_degree = sh_degree; view.campos = vd + 32; view.prefiltered = 0; view.debug = 0;
-        if (images_host && v >= 2) GS_CUDA_CHECK(cudaStreamWaitEvent(s, C.img_copied[b], 0));
-        gs_b200_state st;
-        float* img = d_img[b];
-        if (gs_b200_rasterize_forward(&view, N, M, d_means, d_shs, nullptr, d_opac, d_scales, d_rots, nullptr, img,
-                                      img + 3 * npix, img + 4 * npix, d_radii, nullptr, nullptr, &st, s)) return 1;
-        rendered += st.num_rendered;
-        if (images_host) {
-            GS_CUDA_CHECK(cudaEventRecord(C.img_ready[b], s));
-            GS_CUDA_CHECK(cudaStreamWaitEvent(C.copy_stream, C.img_ready[b], 0));
-            GS_CUDA_CHECK(cudaMemcpyAsync(images_host + (size_t)v * 5 * npix, img, 5 * npix * 4, cudaMemcpyDeviceToHost, C.copy_stream));
-            GS_CUDA_CHECK(cudaEventRecord(C.img_copied[b], C.copy_stream));
-        }
-        GS_CUDA_CHECK(cudaStreamWaitEvent(s, C.up_done[b], 0));
-        const float* up = d_up[b];
-        int rc = gs_b200_rasterize_backward(&view, N, M, d_means, d_shs, nullptr, d_opac, d_scales, d_rots, nullptr,
-                                            d_radii, &st, up, up + 3 * npix, up + 4 * npix, g_means, g_m2d, g_shs,
-                                            nullptr, g_opac, g_scales, g_rots, nullptr, 1, nullptr, nullptr, s);
-        GS_CUDA_CHECK(cudaEventRecord(C.consumed[b], s));
-        gs_b200_state_free(&st, s);
-        if (rc) return 1;
+    float* d_up = c.take<float>((size_t)V * 5 * npix);
+    float* d_img = images_host ? c.take<float>((size_t)V * 5 * npix) : nullptr;
+    const PackedPtrs par = carve_packed(d_par, N, M, false), grd = carve_packed(d_grad, N, M, true);
+    while ((int)C.up_ready.size() < V) {
+        cudaEvent_t e; GS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); C.up_ready.push_back(e);
     }
+    // upstream gradients stream in on the copy engine, view by view, behind the compute
+    GS_CUDA_CHECK(cudaEventRecord(C.evFork, s));
+    GS_CUDA_CHECK(cudaStreamWaitEvent(C.copy_stream, C.evFork, 0));
+    for (int v = 0; v < V; v++) {
+        GS_CUDA_CHECK(cudaMemcpyAsync(d_up + (size_t)v * 5 * npix, dL_dout_host + (size_t)v * 5 * npix, 5 * npix * 4,
+                                      cudaMemcpyHostToDevice, C.copy_stream));
+        GS_CUDA_CHECK(cudaEventRecord(C.up_ready[v], C.copy_stream));
+    }
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.means, means3D_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.opac, opacities_host, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.scales, scales_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.rots, rotations_host, (size_t)N * 16, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemcpyAsync(d_views, views_host, (size_t)V * 160, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.shs, shs_host, (size_t)N * 12 * M, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaMemsetAsync(d_grad, 0, n_grad * 4, s));
+    if (step_core(V, H, W, sh_degree, scale_modifier, views_host, d_views, N, M, par, d_up, C.up_ready.data(), grd,
+                  d_img, num_rendered_out, s)) return 1;
     if (grads_dev) GS_CUDA_CHECK(cudaMemcpyAsync(grads_dev, d_grad, n_grad * 4, cudaMemcpyDeviceToDevice, s));
     if (grads_host) GS_CUDA_CHECK(cudaMemcpyAsync(grads_host, d_grad, n_grad * 4, cudaMemcpyDeviceToHost, s));
-    GS_CUDA_CHECK(cudaStreamSynchronize(C.copy_stream));
-    if (grads_host) GS_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (num_rendered_out) *num_rendered_out = rendered;
+    if (images_host) GS_CUDA_CHECK(cudaMemcpyAsync(images_host, d_img, (size_t)V * 5 * npix * 4, cudaMemcpyDeviceToHost, s));
+    if (grads_host || images_host) GS_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
+}
+}  // namespace
+
+int32_t gs_b200_step_device(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                            const float* views_host, const float* views_dev, int32_t N, int32_t M,
+                            const float* means3D, const float* shs, const float* opacities, const float* scales,
+                            const float* rotations, const float* dL_dout, float* grads, float* images,
+                            int64_t* num_rendered_out, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !shs || !opacities || !scales || !rotations ||
+        !dL_dout || !grads) { gs_set_error("step_device: bad argument"); return 1; }
+    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
+    par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
+    const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
+    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    const PackedPtrs grd = carve_packed(grads, N, M, true);
+    return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
+                     num_rendered_out, s);
 }
 
 int32_t gs_b200_step_host(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,

@@ -27,14 +27,15 @@
 // gathered (3 x LDG.128) by the composite kernels.
 struct __align__(16) SplatRec {
     float4 g;   // px, py, depth, radius(int bits)
-    float4 c;   // conic a, b, c, opacity
+    float4 c;   // conic pre-scaled to log2 units: -0.5*log2e*A, -log2e*B, -0.5*log2e*C ; opacity
     float4 k;   // r, g, b, tiles_touched(uint bits)
 };
 
 // Per-Gaussian gradient accumulator filled by the composite backward (atomics).
 struct __align__(16) SplatGrad {
-    float4 g;   // dL/dpx, dL/dpy, dL/ddepth, -
-    float4 c;   // dL/dconic a, b, c (true partials), dL/dopacity
+    // raw moment sums over the pixels a splat was blended into, w = dL/dG * G, d = mean2D - pixel:
+    float4 g;   // sum w*dx, sum w*dy, dL/ddepth, -
+    float4 c;   // sum w*dx*dx, sum w*dx*dy, sum w*dy*dy, dL/dopacity
     float4 k;   // dL/dr, dL/dg, dL/db, -
 };
 

@@ -169,7 +169,9 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
                     sh_to_rgb(va.sh_degree, M, s_sh + tid * rowp, x - s_cam[0], y - s_cam[1], z - s_cam[2], cr, cg, cbl);
                 }
                 rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
-                rec.c = make_float4(cc * det_inv, -cb * det_inv, ca * det_inv, opacities[idx]);
+                // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
+                const float L2E = 1.4426950408889634f;
+                rec.c = make_float4(-0.5f * L2E * (cc * det_inv), L2E * (cb * det_inv), -0.5f * L2E * (ca * det_inv), opacities[idx]);
                 rec.k = make_float4(cr, cg, cbl, __uint_as_float(tiles));
             }
         }

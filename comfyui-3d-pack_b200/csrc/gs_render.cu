@@ -6,32 +6,70 @@
 // power>0 or alpha<1/255; stop WITHOUT blending when T(1-alpha) < 1e-4;
 // color = C + T*bg, depth = sum(depth*alpha*T), alpha_out = sum(alpha*T).
 //
-// Design (sm_100a):
+// Design (sm_100a) — both kernels are instruction-issue bound, not HBM bound
+// (the splat records, 48 MB, live in the 126 MB L2), so everything here is about
+// issuing fewer instructions per (pixel, splat):
 //  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel sub-rect;
-//  * a batch of 256 splat records is gathered with 3 x LDG.128 per record into
-//    shared memory; while it is staged, the loading thread computes for its splat
-//    an 8-bit mask "can reach alpha>=1/255 inside warp w's sub-rect" from the
-//    exact minimum of the quadratic form over the rectangle (conservative by a
-//    slack), so each warp only walks the splats that can touch its 32 pixels —
-//    the results are unchanged because a skipped splat would have failed the
-//    per-pixel alpha test on every lane anyway;
-//  * backward: per-splat partial gradients are reduced over the warp's 32
-//    pixels with shuffles and leave the SM as one red.global.add per value.
+//  * a batch of 256 records (3 x LDG.128 each) is staged in shared memory as
+//    48 B AoS; while staging, the loading thread computes for its splat an 8-bit
+//    mask "can reach alpha >= 1/255 inside warp w's sub-rect" from the exact
+//    minimum of the quadratic form over the rectangle (+ slack), so each warp
+//    only walks the ~11 % of (warp, splat) pairs that can touch its 32 pixels.
+//    Results are unchanged: a skipped splat fails the per-pixel alpha test on
+//    every lane anyway;
+//  * the record holds the conic pre-scaled to log2 units (a' = -0.5*log2e*A,
+//    b' = -log2e*B, c' = -0.5*log2e*C) so power is 2 FMUL + 2 FFMA + 1 FMUL and
+//    exp is a bare ex2.approx (MUFU.EX2);
+//  * backward: per-pixel partials are raw moment sums (sum w dx, sum w dx dx ...,
+//    w = dL/dG * G) — the constant factors and the conic multiplications move to
+//    the per-Gaussian preprocess backward; the 10 sums are reduced over the 32
+//    lanes with a TRANSPOSE butterfly (12 SHFL instead of 50) that leaves each
+//    total in its own lane, so ONE red.global.add instruction with 10 active
+//    lanes updates the 48 B gradient record.
 #include "gs_common.cuh"
 
 namespace {
 
 constexpr int RB = 256;   // threads per CTA == splats per batch
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr uint32_t REC_BYTES = 48;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// power in log2 units from the pre-scaled conic; identical code in forward and
+// backward so both make the same skip decisions.
+__device__ __forceinline__ float power2_of(const float4 c, float dx, float dy) {
+    float t = c.x * dx;
+    t = fmaf(c.y, dy, t);
+    float p = t * dx;
+    return fmaf(c.z * dy, dy, p);
+}
 
 // 8-bit mask over the CTA's warps: bit w set if the splat may contribute in
 // sub-rect w (x in [ox+8*(w&1), +7], y in [oy+4*(w>>1), +3]).
 __device__ __forceinline__ uint32_t subrect_mask(const float4 g, const float4 c, int ox, int oy) {
     const float o = c.w;
     if (!(o * 255.0f >= 1.0f) || __float_as_int(g.w) <= 0) return 0u;   // can never reach 1/255 (also NaN)
-    // contributes iff q(d) = 0.5(A dx^2 + C dy^2) + B dx dy <= tau ;  slack covers fp32 rounding
-    const float tau = __logf(o * 255.0f) * 1.001f + 0.02f;
-    const float A = c.x, B = c.y, C = c.z;
+    // contributes iff q(u) = 0.5(A u_x^2 + C u_y^2) + B u_x u_y <= tau (log2 units); slack covers fp32 rounding
+    const float tau = __log2f(o * 255.0f) * 1.001f + 0.03f;
+    const float A = -2.0f * c.x, B = -c.y, C = -2.0f * c.z;
     if (!(A > 0.f && A * C - B * B > 0.f)) return 0xFFu;   // not positive definite: no culling, per-pixel test decides
     const float invA = 1.0f / A, invC = 1.0f / C;
     uint32_t mask = 0;
@@ -60,13 +98,23 @@ __device__ __forceinline__ uint32_t subrect_mask(const float4 g, const float4 c,
     return mask;
 }
 
+// stage one batch: thread t loads record of list position (first + t)
+__device__ __forceinline__ uint32_t stage_record(const SplatRec* __restrict__ recs, uint32_t id, uint32_t s_rec,
+                                                 int tid, int ox, int oy) {
+    const float4 g = __ldg(&recs[id].g), c = __ldg(&recs[id].c), k = __ldg(&recs[id].k);
+    const uint32_t a = s_rec + tid * REC_BYTES;
+    sts128(a, g); sts128(a + 16, c); sts128(a + 32, k);
+    return subrect_mask(g, c, ox, oy);
+}
+
 __global__ void __launch_bounds__(RB)
 render_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                       const uint32_t* __restrict__ ranges, float* __restrict__ out_color,
                       float* __restrict__ out_depth, float* __restrict__ out_alpha,
                       uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
-    __shared__ float4 s_g[RB], s_c[RB], s_k[RB];
+    __shared__ __align__(16) unsigned char s_rec_raw[RB * REC_BYTES];
     __shared__ uint32_t s_mask[RB];
+    const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(s_rec_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ox = blockIdx.x * GS_TILE, oy = blockIdx.y * GS_TILE;
     const int px = ox + 8 * (warp & 1) + (lane & 7);
@@ -83,40 +131,29 @@ render_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint
     for (uint32_t base = start; base < end; base += RB) {
         if (__syncthreads_count(done) == RB) break;
         const int n = min((uint32_t)RB, end - base);
-        if (tid < n) {
-            const uint32_t id = __ldg(point_list + base + tid);
-            const float4 g = __ldg(&recs[id].g), c = __ldg(&recs[id].c), k = __ldg(&recs[id].k);
-            s_g[tid] = g; s_c[tid] = c; s_k[tid] = k;
-            s_mask[tid] = subrect_mask(g, c, ox, oy);
-        }
+        if (tid < n) s_mask[tid] = stage_record(recs, __ldg(point_list + base + tid), s_rec, tid, ox, oy);
         __syncthreads();
+        const uint32_t pos0 = base - start + 1;
         for (int k0 = 0; k0 < n; k0 += 32) {
             const uint32_t mine = (k0 + lane < n) ? ((s_mask[k0 + lane] >> warp) & 1u) : 0u;
             uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
             while (bal) {
                 const int j = k0 + __ffs(bal) - 1;
                 bal &= bal - 1;
-                if (!done) {
-                    const float4 g = s_g[j], c = s_c[j];
-                    const float dx = g.x - pxf, dy = g.y - pyf;
-                    const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
-                    if (power <= 0.f) {
-                        const float alpha = fminf(0.99f, c.w * __expf(power));
-                        if (alpha >= ALPHA_MIN) {
-                            const float test_T = T * (1.f - alpha);
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                const float4 k = s_k[j];
-                                const float w = alpha * T;
-                                C0 += k.x * w; C1 += k.y * w; C2 += k.z * w;
-                                D += g.z * w; Aacc += w;
-                                T = test_T;
-                                last = base - start + j + 1;
-                            }
-                        }
-                    }
-                }
+                const uint32_t ra = s_rec + j * REC_BYTES;
+                const float4 g = lds128(ra), c = lds128(ra + 16);
+                const float dx = g.x - pxf, dy = g.y - pyf;
+                const float p2 = power2_of(c, dx, dy);
+                const float alpha = fminf(0.99f, c.w * ex2_approx(p2));
+                if (done || !(p2 <= 0.f) || alpha < ALPHA_MIN) continue;
+                const float test_T = T * (1.f - alpha);
+                if (test_T < 0.0001f) { done = true; continue; }
+                const float4 k = lds128(ra + 32);
+                const float w = alpha * T;
+                C0 = fmaf(k.x, w, C0); C1 = fmaf(k.y, w, C1); C2 = fmaf(k.z, w, C2);
+                D = fmaf(g.z, w, D); Aacc += w;
+                T = test_T;
+                last = pos0 + j;
             }
             if (__all_sync(0xFFFFFFFFu, done)) break;
         }
@@ -135,21 +172,24 @@ render_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
+// One butterfly stage of the transpose reduction: lanes whose `bit` is clear keep
+// a (and receive the partner's a), lanes whose bit is set keep b.
+__device__ __forceinline__ float xstage(float a, float b, bool hi, int m) {
+    const float send = hi ? a : b;
+    const float keep = hi ? b : a;
+    return keep + __shfl_xor_sync(0xFFFFFFFFu, send, m);
 }
 
-__global__ void __launch_bounds__(RB)
+__global__ void __launch_bounds__(RB, 3)
 render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                        const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
                        const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                        SplatGrad* __restrict__ sg) {
-    __shared__ float4 s_g[RB], s_c[RB], s_k[RB];
+    __shared__ __align__(16) unsigned char s_rec_raw[RB * REC_BYTES];
     __shared__ uint32_t s_mask[RB], s_id[RB];
     __shared__ uint32_t s_max;
+    const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(s_rec_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ox = blockIdx.x * GS_TILE, oy = blockIdx.y * GS_TILE;
     const int px = ox + 8 * (warp & 1) + (lane & 7);
@@ -169,38 +209,38 @@ render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uin
         gC0 = dL_dcolor[pix]; gC1 = dL_dcolor[plane + pix]; gC2 = dL_dcolor[2 * plane + pix];
         gD = dL_ddepth[pix]; gA = dL_dalpha[pix];
     }
-    const float bg_dot = __ldg(va.bg) * gC0 + __ldg(va.bg + 1) * gC1 + __ldg(va.bg + 2) * gC2;
+    const float bgT = -T_final * (__ldg(va.bg) * gC0 + __ldg(va.bg + 1) * gC1 + __ldg(va.bg + 2) * gC2);
+
+    // transpose-reduction lane roles: value index held by this lane after the 5 stages
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+    const int sub = (h8 ? 3 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+    const bool my_valid = !(lane & 1) && !(h8 && h4) && !(!h8 && h4 && h2);
+    const int vi = (h16 ? 5 : 0) + sub;                       // 0..9
+    const int my_off = vi + (vi >= 3);                        // float offset inside SplatGrad (skips g.w)
 
     if (tid == 0) s_max = 0;
     __syncthreads();
-    {
-        uint32_t m = last_contrib;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-        if (lane == 0 && m) atomicMax(&s_max, m);
-    }
-    __syncthreads();
-    const uint32_t nproc = s_max;        // only positions 1..nproc were blended by some pixel
-    if (nproc == 0) return;
-    // warp-level bound as well: nothing above this warp's own max was blended by its pixels
     uint32_t wmax = last_contrib;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+    if (lane == 0 && wmax) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const uint32_t nproc = s_max;        // only list positions 1..nproc were blended by some pixel of the tile
+    if (nproc == 0) return;
 
     float T = T_final;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
 
-    // batches from the back: batch b covers list positions (0-based) [lo, hi)
+    // batches from the back: a batch covers 0-based list positions [lo, hi)
     for (int hi = (int)nproc; hi > 0; hi -= RB) {
         const int lo = max(0, hi - RB);
         const int n = hi - lo;
         __syncthreads();
         if (tid < n) {
             const uint32_t id = __ldg(point_list + start + lo + tid);
-            const float4 g = __ldg(&recs[id].g), c = __ldg(&recs[id].c), k = __ldg(&recs[id].k);
-            s_g[tid] = g; s_c[tid] = c; s_k[tid] = k; s_id[tid] = id;
-            s_mask[tid] = subrect_mask(g, c, ox, oy);
+            s_id[tid] = id;
+            s_mask[tid] = stage_record(recs, id, s_rec, tid, ox, oy);
         }
         __syncthreads();
         for (int k0 = ((n - 1) >> 5) << 5; k0 >= 0; k0 -= 32) {
@@ -211,53 +251,49 @@ render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uin
                 const int jb = 31 - __clz(bal);
                 bal &= ~(1u << jb);
                 const int j = k0 + jb;
-                const uint32_t pos1 = (uint32_t)(lo + j) + 1u;       // 1-based list position
-                const float4 g = s_g[j], c = s_c[j];
+                const uint32_t ra = s_rec + j * REC_BYTES;
+                const float4 g = lds128(ra), c = lds128(ra + 16);
                 const float dx = g.x - pxf, dy = g.y - pyf;
-                const float power = -0.5f * (c.x * dx * dx + c.z * dy * dy) - c.y * dx * dy;
-                const float G = __expf(power);
+                const float p2 = power2_of(c, dx, dy);
+                const float G = ex2_approx(p2);
                 const float alpha = fminf(0.99f, c.w * G);
-                const bool active = (pos1 <= last_contrib) && (power <= 0.f) && (alpha >= ALPHA_MIN);
+                const bool active = ((uint32_t)(lo + j) < last_contrib) && (p2 <= 0.f) && !(alpha < ALPHA_MIN);
                 if (!__any_sync(0xFFFFFFFFu, active)) continue;
-                float v_mx = 0.f, v_my = 0.f, v_ca = 0.f, v_cb = 0.f, v_cc = 0.f, v_op = 0.f;
-                float v_r = 0.f, v_g = 0.f, v_b = 0.f, v_d = 0.f;
+                // raw moment sums; constants and conic factors are applied per Gaussian in preprocess_backward
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
                 if (active) {
-                    const float4 k = s_k[j];
-                    T = T / (1.f - alpha);
+                    const float4 k = lds128(ra + 32);
+                    const float ria = rcp_approx(1.f - alpha);
+                    T *= ria;
                     const float dchan = alpha * T;
-                    float dL_da = 0.f;
-                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = k.x;
-                    dL_da += (k.x - acc0) * gC0; v_r = dchan * gC0;
-                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = k.y;
-                    dL_da += (k.y - acc1) * gC1; v_g = dchan * gC1;
-                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = k.z;
-                    dL_da += (k.z - acc2) * gC2; v_b = dchan * gC2;
-                    accD = last_alpha * lD + (1.f - last_alpha) * accD; lD = g.z;
-                    dL_da += (g.z - accD) * gD; v_d = dchan * gD;
-                    accA = last_alpha + (1.f - last_alpha) * accA;
-                    dL_da += (1.f - accA) * gA;
-                    dL_da *= T;
+                    acc0 = fmaf(last_alpha, lc0 - acc0, acc0); lc0 = k.x;
+                    acc1 = fmaf(last_alpha, lc1 - acc1, acc1); lc1 = k.y;
+                    acc2 = fmaf(last_alpha, lc2 - acc2, acc2); lc2 = k.z;
+                    accD = fmaf(last_alpha, lD - accD, accD); lD = g.z;
+                    accA = fmaf(last_alpha, 1.f - accA, accA);
+                    float dL_da = (k.x - acc0) * gC0;
+                    dL_da = fmaf(k.y - acc1, gC1, dL_da);
+                    dL_da = fmaf(k.z - acc2, gC2, dL_da);
+                    dL_da = fmaf(g.z - accD, gD, dL_da);
+                    dL_da = fmaf(1.f - accA, gA, dL_da);
+                    dL_da = fmaf(dL_da, T, bgT * ria);      // *T, + (-T_final/(1-alpha)) * bg.dL_dpixel
                     last_alpha = alpha;
-                    dL_da += (-T_final / (1.f - alpha)) * bg_dot;
                     // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6)
-                    const float dL_dG = c.w * dL_da;
-                    const float gdx = G * dx, gdy = G * dy;
-                    v_mx = dL_dG * (-gdx * c.x - gdy * c.y);
-                    v_my = dL_dG * (-gdy * c.z - gdx * c.y);
-                    v_ca = -0.5f * gdx * dx * dL_dG;
-                    v_cb = -gdx * dy * dL_dG;
-                    v_cc = -0.5f * gdy * dy * dL_dG;
-                    v_op = G * dL_da;
+                    const float gda = G * dL_da;
+                    const float w = c.w * gda;              // dL/dG * G
+                    const float wx = w * dx, wy = w * dy;
+                    v0 = wx; v1 = wy; v2 = dchan * gD;
+                    v3 = wx * dx; v4 = wx * dy; v5 = wy * dy; v6 = gda;
+                    v7 = dchan * gC0; v8 = dchan * gC1; v9 = dchan * gC2;
                 }
-                v_mx = warp_sum(v_mx); v_my = warp_sum(v_my); v_d = warp_sum(v_d);
-                v_ca = warp_sum(v_ca); v_cb = warp_sum(v_cb); v_cc = warp_sum(v_cc); v_op = warp_sum(v_op);
-                v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
-                if (lane == 0) {
-                    float* dst = reinterpret_cast<float*>(sg + s_id[j]);
-                    atomicAdd(dst + 0, v_mx); atomicAdd(dst + 1, v_my); atomicAdd(dst + 2, v_d);
-                    atomicAdd(dst + 4, v_ca); atomicAdd(dst + 5, v_cb); atomicAdd(dst + 6, v_cc); atomicAdd(dst + 7, v_op);
-                    atomicAdd(dst + 8, v_r); atomicAdd(dst + 9, v_g); atomicAdd(dst + 10, v_b);
-                }
+                // transpose butterfly: 10 -> 5 -> 3 -> 2 -> 1 values per lane
+                const float u0 = xstage(v0, v5, h16, 16), u1 = xstage(v1, v6, h16, 16), u2 = xstage(v2, v7, h16, 16),
+                            u3 = xstage(v3, v8, h16, 16), u4 = xstage(v4, v9, h16, 16);
+                const float t0 = xstage(u0, u3, h8, 8), t1 = xstage(u1, u4, h8, 8), t2 = xstage(u2, 0.f, h8, 8);
+                const float s0 = xstage(t0, t2, h4, 4), s1 = xstage(t1, 0.f, h4, 4);
+                float r = xstage(s0, s1, h2, 2);
+                r += __shfl_xor_sync(0xFFFFFFFFu, r, 1);
+                if (my_valid) atomicAdd(reinterpret_cast<float*>(sg + s_id[j]) + my_off, r);
             }
         }
     }

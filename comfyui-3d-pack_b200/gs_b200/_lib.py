@@ -59,6 +59,9 @@ lib.gs_b200_step_host.restype = C.c_int32
 lib.gs_b200_step_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, C.c_int32, C.c_int32] + \
     [_P] * 5 + [_P, _P, _P, C.POINTER(C.c_int64), _P]
 
+lib.gs_b200_step_device.restype = C.c_int32
+lib.gs_b200_step_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
+    [_P] * 5 + [_P, _P, _P, C.POINTER(C.c_int64), _P]
 lib.gs_b200_step_host_dev_grads.restype = C.c_int32
 lib.gs_b200_step_host_dev_grads.argtypes = lib.gs_b200_step_host.argtypes
 lib.gs_b200_launch_count.restype = C.c_int64
@@ -70,7 +73,7 @@ NSTAGES = 9
 STAGE_NAMES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "composite_fwd",
                "composite_bwd", "preprocess_bwd"]
 
-EXPORTS = ["gs_b200_step_host_dev_grads", "gs_b200_launch_count", "gs_b200_profile_enable", "gs_b200_profile_read",
+EXPORTS = ["gs_b200_step_device", "gs_b200_step_host_dev_grads", "gs_b200_launch_count", "gs_b200_profile_enable", "gs_b200_profile_read",
            "gs_b200_abi_version", "gs_b200_last_error", "gs_b200_rasterize_forward", "gs_b200_rasterize_backward",
            "gs_b200_state_free", "gs_b200_debug_sorted_keys", "gs_b200_sort_scratch_bytes",
            "gs_b200_sort_pairs_u32", "gs_b200_knn_mean_dist2", "gs_b200_step_host"]

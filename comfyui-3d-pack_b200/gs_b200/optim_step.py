@@ -99,6 +99,20 @@ def step_device(params: PackedParams, views: ViewSet, dL_dout: torch.Tensor, out
     return total_pairs
 
 
+def step_device_pipelined(params: PackedParams, views: ViewSet, dL_dout: torch.Tensor, out_images: torch.Tensor = None):
+    """Same contract as step_device, through the C entry gs_b200_step_device: views software-pipelined over two
+    internal streams with persistent workspaces (no per-view allocation, host pair-count wait hidden)."""
+    import numpy as np
+    assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
+    pairs = C.c_int64(0)
+    _lib.check(_lib.lib.gs_b200_step_device(
+        views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
+        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+        _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads),
+        None if out_images is None else _ptr(out_images), C.byref(pairs), _stream()))
+    return int(pairs.value)
+
+
 class HostStep:
     """The e2e entry (gs_b200_step_host): pinned host buffers in, summed gradients out."""
 

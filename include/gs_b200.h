@@ -136,6 +136,19 @@ int32_t gs_b200_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* val
  * mean squared distance to the 3 nearest neighbours. points[N,3] -> out[N]. */
 int32_t gs_b200_knn_mean_dist2(const float* points, int32_t N, float* out, void* stream);
 
+/* Multi-view optimisation step with DEVICE-resident buffers: V x (forward + backward), gradients
+ * summed over views into `grads` (zeroed first), packed as
+ *   means3D[N,3] | shs[N,M,3] | opacities[N] | scales[N,3] | rotations[N,4] | means2D[N,3]
+ * (the buffer a data-parallel caller all-reduces).  Views are software-pipelined over two internal
+ * streams with persistent workspaces; all work is ordered after `stream` and `stream` continues after it.
+ *   views_host / views_dev: the same V x 40 floats (layout below) in host and device memory
+ *   dL_dout: device V x [5,H,W]; images: optional device V x [5,H,W] output (NULL = not kept) */
+int32_t gs_b200_step_device(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* opacities,
+    const float* scales, const float* rotations, const float* dL_dout, float* grads, float* images,
+    int64_t* num_rendered_out, void* stream);
+
 /* Multi-view optimisation step with HOST buffers (the e2e entry: H2D of the
  * Gaussians, V x (forward + backward) with gradients summed over views on the
  * device, D2H of the summed gradients).  Host pointers should be pinned.
