@@ -13,26 +13,54 @@
 
 namespace {
 
-// One thread per depth-sorted Gaussian; writes its run of tiles row-major.
-__global__ void __launch_bounds__(256)
+// Each warp takes 32 consecutive depth-sorted Gaussians.  Their output runs are back to back
+// ([offsets[s0], offsets[s0+32]) is one contiguous span), so the lanes sweep that span with fully
+// coalesced stores and find the owning Gaussian of each slot by binary search over the 32 offsets.
+constexpr int EMIT_WARPS = 8;
+__global__ void __launch_bounds__(EMIT_WARPS * 32)
 emit_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ sorted_ids,
             const uint32_t* __restrict__ offsets, int N, int tiles_x, int tiles_y,
             uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= N) return;
-    const uint32_t idx = sorted_ids[s];
-    const float4 g = __ldg(&recs[idx].g);
-    const int radius = __float_as_int(g.w);
-    if (radius <= 0) return;
-    int x0, y0, x1, y1;
-    get_rect(g.x, g.y, radius, tiles_x, tiles_y, x0, y0, x1, y1);
-    uint32_t off = offsets[s];
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            tile_keys[off] = (uint32_t)(y * tiles_x + x);
-            vals[off] = idx;
-            off++;
+    __shared__ uint32_t s_off[EMIT_WARPS][33];
+    __shared__ int s_x0[EMIT_WARPS][32], s_y0[EMIT_WARPS][32], s_w[EMIT_WARPS][32];
+    __shared__ uint32_t s_idx[EMIT_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s0 = (blockIdx.x * EMIT_WARPS + warp) * 32;
+    if (s0 >= N) return;
+    const int s = s0 + lane;
+    uint32_t idx = 0, off = 0, cnt = 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (s < N) {
+        idx = sorted_ids[s];
+        off = offsets[s];
+        const float4 g = __ldg(&recs[idx].g);
+        const int radius = __float_as_int(g.w);
+        if (radius > 0) {
+            get_rect(g.x, g.y, radius, tiles_x, tiles_y, x0, y0, x1, y1);
+            cnt = (uint32_t)((x1 - x0) * (y1 - y0));
         }
+    }
+    // lanes past N inherit the end of the span so the offsets stay non-decreasing
+    const uint32_t endv = off + cnt;
+    const int last = min(31, N - 1 - s0);
+    const uint32_t span_end = __shfl_sync(0xFFFFFFFFu, endv, last);
+    if (s >= N) off = span_end;
+    s_off[warp][lane] = off; s_x0[warp][lane] = x0; s_y0[warp][lane] = y0; s_w[warp][lane] = x1 - x0; s_idx[warp][lane] = idx;
+    if (lane == 0) s_off[warp][32] = span_end;
+    __syncwarp();
+    const uint32_t base = s_off[warp][0];
+    for (uint32_t t = base + lane; t < span_end; t += 32) {
+        // largest L with s_off[L] <= t  (zero-count entries share an offset with their successor: skipped naturally)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_off[warp][lo + step] <= t) lo += step;
+        const uint32_t local = t - s_off[warp][lo];
+        const int w = s_w[warp][lo];
+        const int ry = (int)local / w, rx = (int)local - ry * w;
+        tile_keys[t] = (uint32_t)((s_y0[warp][lo] + ry) * tiles_x + s_x0[warp][lo] + rx);
+        vals[t] = s_idx[warp][lo];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -62,7 +90,7 @@ sorted_keys_kernel(const SplatRec* __restrict__ recs, const uint32_t* __restrict
 int gs_launch_emit(const SplatRec* recs, const uint32_t* sorted_ids, const uint32_t* offsets, int N,
                    int tiles_x, int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s) {
     if (N <= 0) return 0;
-    emit_kernel<<<(N + 255) / 256, 256, 0, s>>>(recs, sorted_ids, offsets, N, tiles_x, tiles_y, tile_keys, vals);
+    emit_kernel<<<(N + EMIT_WARPS * 32 - 1) / (EMIT_WARPS * 32), EMIT_WARPS * 32, 0, s>>>(recs, sorted_ids, offsets, N, tiles_x, tiles_y, tile_keys, vals);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -231,7 +231,7 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
     *host_total = 0;
     if (N > 0) {
         const size_t sort_b = gs_sort_scratch_bytes(N), scan_b = gs_scan_scratch_bytes(N);
-        const size_t sc_bytes = Carver::need(N, 4) * 6 + Carver::need(1, 8) + Carver::need(sort_b, 1) + Carver::need(scan_b, 1);
+        const size_t sc_bytes = Carver::need(N, 4) * 6 + Carver::need(1, 8) * 2 + Carver::need(sort_b, 1) + Carver::need(scan_b, 1);
         void* sc = A.get(GS_B200_BUF_SCRATCH, sc_bytes);
         if (A.failed) return 1;
         Carver cv(sc);
@@ -242,15 +242,17 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
         uint32_t* ids_alt = cv.take<uint32_t>(N);
         c.offsets = cv.take<uint32_t>(N);
         unsigned long long* total = cv.take<unsigned long long>(1);
+        uint32_t* min_key = (uint32_t*)cv.take<unsigned long long>(1);
         void* sort_scratch = cv.take<char>(sort_b);
+        GS_CUDA_CHECK(cudaMemsetAsync(min_key, 0xFF, 4, s));
         void* scan_scratch = cv.take<char>(scan_b);
         { StageTimer t(0, s);
         if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 c.recs, radii, tiles, dkeys, ids, s)) return 1; }
+                                 c.recs, radii, tiles, dkeys, ids, min_key, s)) return 1; }
         STAGE_CHECK(c.dbg, s, "preprocess");
         int in_alt = 0;
         { StageTimer t(1, s);
-        if (gs_sort_pairs_u32(dkeys, dkeys_alt, ids, ids_alt, N, 0, 32, sort_scratch, &in_alt, s)) return 1; }
+        if (gs_sort_pairs_u32_biased(dkeys, dkeys_alt, ids, ids_alt, N, 0, 32, sort_scratch, &in_alt, min_key, s)) return 1; }
         STAGE_CHECK(c.dbg, s, "depth sort");
         c.sorted_ids = in_alt ? ids_alt : ids;
         { StageTimer t(2, s);

@@ -137,7 +137,8 @@ void gs_count_launches(int n);     // instrumentation: kernels launched by this 
 int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,
                          const float* colors_precomp, const float* opacities, const float* scales,
                          const float* rotations, const float* cov3D_precomp, SplatRec* recs, int32_t* radii,
-                         uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, cudaStream_t s);
+                         uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_key,
+                         cudaStream_t s);
 
 int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,
                                   const float* colors_precomp, const float* opacities, const float* scales,
@@ -149,6 +150,10 @@ int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float*
 size_t gs_sort_scratch_bytes(int64_t n);
 int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
                       int begin_bit, int end_bit, void* scratch, int* result_in_alt, cudaStream_t s);
+
+int gs_sort_pairs_u32_biased(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
+                             int begin_bit, int end_bit, void* scratch, int* result_in_alt,
+                             const uint32_t* key_bias, cudaStream_t s);
 
 size_t gs_scan_scratch_bytes(int64_t n);
 // offsets[i] = exclusive prefix of tiles[ids[i]] (ids may be NULL -> identity); total[0] = sum.

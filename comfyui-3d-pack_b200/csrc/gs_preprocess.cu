@@ -64,11 +64,13 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
                   const float* __restrict__ scales, const float* __restrict__ rotations,
                   const float* __restrict__ cov3D_precomp, SplatRec* __restrict__ recs,
                   int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids) {
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, uint32_t* __restrict__ min_key) {
     extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_view[16], s_proj[16], s_cam[3];
+    __shared__ uint32_t s_min;
     const int tid = threadIdx.x;
     const int base = blockIdx.x * PP_THREADS;
+    if (tid == 0) s_min = 0xFFFFFFFFu;
     if (tid < 16) { s_view[tid] = __ldg(va.view + tid); s_proj[tid] = __ldg(va.proj + tid); }
     if (tid < 3) s_cam[tid] = __ldg(va.campos + tid);
 
@@ -78,8 +80,8 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
         gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
     __syncthreads();
 
-    const int idx = base + tid;
-    if (idx >= N) return;
+    const bool live = base + tid < N;
+    const int idx = live ? base + tid : N - 1;      // tail threads redo the last Gaussian, stores are guarded
     const float* m = s_view;
     const float* p = s_proj;
 
@@ -166,7 +168,7 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
                 if (colors_precomp != nullptr) {
                     cr = colors_precomp[3 * idx + 0]; cg = colors_precomp[3 * idx + 1]; cbl = colors_precomp[3 * idx + 2];
                 } else {
-                    sh_to_rgb(va.sh_degree, M, s_sh + tid * rowp, x - s_cam[0], y - s_cam[1], z - s_cam[2], cr, cg, cbl);
+                    sh_to_rgb(va.sh_degree, M, s_sh + (idx - base) * rowp, x - s_cam[0], y - s_cam[1], z - s_cam[2], cr, cg, cbl);
                 }
                 rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
                 // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
@@ -176,11 +178,17 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
             }
         }
     }
-    recs[idx] = rec;
-    radii[idx] = my_radius;
-    tiles_touched[idx] = tiles;
-    depth_keys[idx] = dkey;
-    ids[idx] = (uint32_t)idx;
+    if (live) {
+        recs[idx] = rec;
+        radii[idx] = my_radius;
+        tiles_touched[idx] = tiles;
+        depth_keys[idx] = dkey;
+        ids[idx] = (uint32_t)idx;
+        if (dkey != 0xFFFFFFFFu) atomicMin(&s_min, dkey);
+    }
+    // minimum visible depth key of the view -> bias of the depth sort (see gs_sort.cu)
+    __syncthreads();
+    if (tid == 0 && s_min != 0xFFFFFFFFu) atomicMin(min_key, s_min);
 }
 
 }  // namespace
@@ -188,7 +196,8 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
 int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,
                          const float* colors_precomp, const float* opacities, const float* scales,
                          const float* rotations, const float* cov3D_precomp, SplatRec* recs, int32_t* radii,
-                         uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, cudaStream_t s) {
+                         uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_key,
+                         cudaStream_t s) {
     if (N <= 0) return 0;
     size_t smem = shs ? (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float) : 0;
     if (smem > 48 * 1024) {
@@ -197,7 +206,7 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
     int blocks = (N + PP_THREADS - 1) / PP_THREADS;
     preprocess_kernel<<<blocks, PP_THREADS, smem, s>>>(va, N, M, means3D, shs, colors_precomp, opacities, scales,
                                                        rotations, cov3D_precomp, recs, radii, tiles_touched,
-                                                       depth_keys, ids);
+                                                       depth_keys, ids, min_key);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -180,7 +180,7 @@ __device__ __forceinline__ float xstage(float a, float b, bool hi, int m) {
     return keep + __shfl_xor_sync(0xFFFFFFFFu, send, m);
 }
 
-__global__ void __launch_bounds__(RB, 3)
+__global__ void __launch_bounds__(RB, 4)
 render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                        const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
@@ -229,8 +229,10 @@ render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uin
     if (nproc == 0) return;
 
     float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accD = 0.f, accA = 0.f;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lD = 0.f;
+    // Upstream gradients are per-pixel constants and the blend is linear in the channels, so the five
+    // "colour behind this splat" recurrences (r,g,b,depth,alpha) of the package collapse into ONE on the
+    // projected scalar s_j = gC.rgb_j + gD*depth_j + gA:  dL/dalpha_j = T_j * (s_j - behind_j) + bg term.
+    float behind = 0.f, last_alpha = 0.f, last_s = 0.f;
 
     // batches from the back: a batch covers 0-based list positions [lo, hi)
     for (int hi = (int)nproc; hi > 0; hi -= RB) {
@@ -266,16 +268,13 @@ render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uin
                     const float ria = rcp_approx(1.f - alpha);
                     T *= ria;
                     const float dchan = alpha * T;
-                    acc0 = fmaf(last_alpha, lc0 - acc0, acc0); lc0 = k.x;
-                    acc1 = fmaf(last_alpha, lc1 - acc1, acc1); lc1 = k.y;
-                    acc2 = fmaf(last_alpha, lc2 - acc2, acc2); lc2 = k.z;
-                    accD = fmaf(last_alpha, lD - accD, accD); lD = g.z;
-                    accA = fmaf(last_alpha, 1.f - accA, accA);
-                    float dL_da = (k.x - acc0) * gC0;
-                    dL_da = fmaf(k.y - acc1, gC1, dL_da);
-                    dL_da = fmaf(k.z - acc2, gC2, dL_da);
-                    dL_da = fmaf(g.z - accD, gD, dL_da);
-                    dL_da = fmaf(1.f - accA, gA, dL_da);
+                    float sj = fmaf(k.x, gC0, gA);
+                    sj = fmaf(k.y, gC1, sj);
+                    sj = fmaf(k.z, gC2, sj);
+                    sj = fmaf(g.z, gD, sj);
+                    behind = fmaf(last_alpha, last_s - behind, behind);
+                    last_s = sj;
+                    float dL_da = sj - behind;
                     dL_da = fmaf(dL_da, T, bgT * ria);      // *T, + (-T_final/(1-alpha)) * bg.dL_dpixel
                     last_alpha = alpha;
                     // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6)

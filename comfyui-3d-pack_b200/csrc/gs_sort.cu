@@ -25,22 +25,33 @@ constexpr int RS_MAX_PASSES = 4;
 constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PFX = 2u << 30, VAL_MASK = (1u << 30) - 1;
 
 // ---- upfront histogram of every digit position -------------------------------
+// key_bias (may be NULL): a device word subtracted from every key before digits are taken.  The depth sort
+// passes the minimum visible depth key, so that the high digit(s) of (key - min) are all zero whenever the
+// depth range spans < 2^24 float steps; such a pass is detected from the histogram (one bin holds all n
+// keys) and degenerates to a straight copy instead of the rank/look-back/scatter chain.
 __global__ void __launch_bounds__(RS_THREADS)
 rs_histogram(const uint32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ ghist, int begin_bit,
-             int npasses) {
+             int npasses, const uint32_t* __restrict__ key_bias) {
     __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += RS_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
+    const uint32_t bias = key_bias ? __ldg(key_bias) : 0u;
     for (int64_t i0 = (int64_t)blockIdx.x * RS_THREADS; i0 < n; i0 += stride) {   // block-uniform trip count
         const int64_t i = i0 + threadIdx.x;
         const bool ok = i < n;
-        const uint32_t k = ok ? __ldg(keys + i) : 0u;
+        const uint32_t k = ok ? (__ldg(keys + i) - bias) : 0u;
+        const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, ok);
         for (int p = 0; p < npasses; p++) {
-            // warp-aggregate: clustered keys (depths, tile runs) would serialise on one bin
-            const uint32_t d = ok ? ((k >> (begin_bit + 8 * p)) & 0xFF) : (0x100u + (threadIdx.x & 31));
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-            if (ok && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&sh[p][d], __popc(peers));
+            // clustered digits (high bits of depths / of tile ids) would serialise 32-way on one shared-memory
+            // bin: when the whole warp agrees, one lane adds the count; otherwise plain shared atomics.
+            const uint32_t d = (k >> (begin_bit + 8 * p)) & 0xFF;
+            const uint32_t d0 = __shfl_sync(0xFFFFFFFFu, d, __ffs(okmask) - 1);
+            if (__all_sync(0xFFFFFFFFu, !ok || d == d0)) {
+                if ((threadIdx.x & 31) == 0 && okmask) atomicAdd(&sh[p][d0], __popc(okmask));
+            } else if (ok) {
+                atomicAdd(&sh[p][d], 1u);
+            }
         }
     }
     __syncthreads();
@@ -50,12 +61,16 @@ rs_histogram(const uint32_t* __restrict__ keys, int64_t n, uint32_t* __restrict_
     }
 }
 
-// exclusive scan of each pass's 256 bins, in place; one CTA per pass
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist(uint32_t* __restrict__ ghist) {
+// exclusive scan of each pass's 256 bins, in place; one CTA per pass.  trivial[p] = 1 when one bin holds all n keys.
+__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist(uint32_t* __restrict__ ghist, uint32_t* __restrict__ trivial,
+                                                         uint32_t n) {
     __shared__ uint32_t s[RS_RADIX];
     uint32_t* h = ghist + blockIdx.x * RS_RADIX;
     const int t = threadIdx.x;
     const uint32_t v = h[t];
+    if (t == 0) trivial[blockIdx.x] = 0;
+    __syncthreads();
+    if (v == n) trivial[blockIdx.x] = 1;
     s[t] = v;
     __syncthreads();
     for (int off = 1; off < RS_RADIX; off <<= 1) {
@@ -82,7 +97,8 @@ __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
             const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
             const uint32_t* __restrict__ ghist_excl, uint32_t* __restrict__ status,
-            uint32_t* __restrict__ ticket) {
+            uint32_t* __restrict__ ticket, const uint32_t* __restrict__ key_bias,
+            const uint32_t* __restrict__ trivial) {
     __shared__ uint32_t s_keys[RS_PART];
     __shared__ uint32_t s_vals[HAS_VALS ? RS_PART : 1];
     __shared__ uint32_t s_whist[RS_WARPS][RS_RADIX];
@@ -92,6 +108,16 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
     __shared__ uint32_t s_part;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (__ldg(trivial)) {          // every key has the same digit here: the stable pass is the identity permutation
+        const int64_t b0 = (int64_t)blockIdx.x * RS_PART;
+#pragma unroll 4
+        for (int i = tid; i < RS_PART; i += RS_THREADS) {
+            const int64_t g = b0 + i;
+            if (g < n) { keys_out[g] = __ldg(keys_in + g); if (HAS_VALS) vals_out[g] = __ldg(vals_in + g); }
+        }
+        return;
+    }
+    const uint32_t bias = key_bias ? __ldg(key_bias) : 0u;
     if (tid == 0) s_part = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
     __syncthreads();
@@ -107,7 +133,7 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
     for (int i = 0; i < RS_ITEMS; i++) {
         const int loc = wbase + i * 32;
         if (loc < valid) {
-            k[i] = __ldg(keys_in + base + loc);
+            k[i] = __ldg(keys_in + base + loc) - bias;
             if (HAS_VALS) v[i] = __ldg(vals_in + base + loc);
         } else {
             k[i] = 0xFFFFFFFFu;   // padding: highest digit, highest index -> lands past `valid`
@@ -190,7 +216,7 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
         if (pos < valid) {
             const uint32_t key = s_keys[pos];
             const int64_t g = s_gbase[(key >> shift) & 0xFF] + pos;
-            keys_out[g] = key;
+            keys_out[g] = key + bias;
             if (HAS_VALS) vals_out[g] = s_vals[pos];
         }
     }
@@ -310,6 +336,13 @@ size_t gs_sort_scratch_bytes(int64_t n) {
 
 int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
                       int begin_bit, int end_bit, void* scratch, int* result_in_alt, cudaStream_t s) {
+    return gs_sort_pairs_u32_biased(keys, keys_alt, vals, vals_alt, n, begin_bit, end_bit, scratch, result_in_alt,
+                                    nullptr, s);
+}
+
+int gs_sort_pairs_u32_biased(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
+                             int begin_bit, int end_bit, void* scratch, int* result_in_alt,
+                             const uint32_t* key_bias, cudaStream_t s) {
     *result_in_alt = 0;
     if (n <= 0 || end_bit <= begin_bit) return 0;
     if (n >= (int64_t)VAL_MASK) { gs_set_error("sort: n too large"); return 1; }
@@ -318,19 +351,20 @@ int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32
     const int64_t parts = (n + RS_PART - 1) / RS_PART;
     uint32_t* ghist = (uint32_t*)scratch;
     uint32_t* tickets = ghist + RS_MAX_PASSES * RS_RADIX;
+    uint32_t* trivial = tickets + 8;
     uint32_t* status = tickets + 64;
     GS_CUDA_CHECK(cudaMemsetAsync(scratch, 0, gs_sort_scratch_bytes(n) - (size_t)(RS_MAX_PASSES - npasses) * parts * RS_RADIX * 4, s));
     int64_t hb = (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8); int hblocks = (int)(hb < 148 * 8 ? hb : 148 * 8);
-    rs_histogram<<<hblocks, RS_THREADS, 0, s>>>(keys, n, ghist, begin_bit, npasses);
-    rs_scan_hist<<<npasses, RS_RADIX, 0, s>>>(ghist);
+    rs_histogram<<<hblocks, RS_THREADS, 0, s>>>(keys, n, ghist, begin_bit, npasses, key_bias);
+    rs_scan_hist<<<npasses, RS_RADIX, 0, s>>>(ghist, trivial, (uint32_t)n);
     uint32_t *kin = keys, *kout = keys_alt, *vin = vals, *vout = vals_alt;
     for (int p = 0; p < npasses; p++) {
         const int shift = begin_bit + 8 * p;
         uint32_t* st = status + (size_t)p * parts * RS_RADIX;
         if (vals)
-            rs_onesweep<true><<<(unsigned)parts, RS_THREADS, 0, s>>>(kin, kout, vin, vout, n, shift, ghist + p * RS_RADIX, st, tickets + p);
+            rs_onesweep<true><<<(unsigned)parts, RS_THREADS, 0, s>>>(kin, kout, vin, vout, n, shift, ghist + p * RS_RADIX, st, tickets + p, key_bias, trivial + p);
         else
-            rs_onesweep<false><<<(unsigned)parts, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, n, shift, ghist + p * RS_RADIX, st, tickets + p);
+            rs_onesweep<false><<<(unsigned)parts, RS_THREADS, 0, s>>>(kin, kout, nullptr, nullptr, n, shift, ghist + p * RS_RADIX, st, tickets + p, key_bias, trivial + p);
         uint32_t* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
         *result_in_alt ^= 1;
