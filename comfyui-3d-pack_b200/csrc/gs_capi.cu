@@ -117,7 +117,8 @@ int make_view_args(const gs_b200_view* v, ViewArgs& va) {
 int check_inputs(int N, int M, int sh_degree, const float* means3D, const float* shs, const float* colors_precomp,
                  const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp) {
     if (N < 0) { gs_set_error("N < 0"); return 1; }
-    if (N > 0 && (!means3D || !opacities)) { gs_set_error("means3D/opacities NULL"); return 1; }
+    if (N == 0) return 0;      // empty cloud: pointers of empty arrays may legitimately be NULL
+    if (!means3D || !opacities) { gs_set_error("means3D/opacities NULL"); return 1; }
     if ((shs == nullptr) == (colors_precomp == nullptr)) {
         gs_set_error("Please provide excatly one of either SHs or precomputed colors!"); return 1;
     }

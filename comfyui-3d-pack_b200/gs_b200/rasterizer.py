@@ -101,6 +101,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raster_settings):
         rs = raster_settings
         dev = means3D.device
+        if dev.type != "cuda":
+            raise RuntimeError("means3D must be a CUDA tensor (gs_b200 has no CPU path)")
         with torch.cuda.device(dev):
             m3 = _dev_f32(means3D, "means3D")
             N = m3.shape[0]

@@ -1,0 +1,293 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test goes through the C ABI
+(libgs_b200.so via ctypes); the CPU oracle is the checker.
+
+Tolerances (BASELINE.json north_star): rendered RGBA within 1e-4 abs, gradients within 1e-3 relative,
+tile/key indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import gs_oracle as O
+
+pytestmark = pytest.mark.gpu
+NAMES = ("means3D", "shs", "opacities", "scales", "rotations")
+RGBA_ATOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def R():
+    from gs_b200 import rasterizer
+    return rasterizer
+
+
+def _rs(R, st, dev, deg, debug=False):
+    return R.GaussianRasterizationSettings(st.image_height, st.image_width, st.tanfovx, st.tanfovy, st.bg.to(dev),
+                                           st.scale_modifier, st.viewmatrix.to(dev), st.projmatrix.to(dev), deg,
+                                           st.campos.to(dev), False, debug)
+
+
+def _upstream(H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(3, H, W, generator=g) * 2 - 1, (torch.rand(1, H, W, generator=g) * 2 - 1) * 0.1,
+            (torch.rand(1, H, W, generator=g) * 2 - 1) * 0.1)
+
+
+def _grad_close(a, b, what):
+    a, b = a.detach().cpu().double(), b.double()
+    scale = float(b.abs().max())
+    if scale == 0.0:
+        assert float(a.abs().max()) < 1e-5, what
+        return
+    rel = float((a - b).norm() / b.norm())
+    assert rel < GRAD_RTOL, f"{what}: relative error {rel}"
+    # element-wise: 1e-3 relative with an absolute floor at 1e-3 of the largest component
+    assert bool(((a - b).abs() <= GRAD_RTOL * b.abs() + 1e-3 * GRAD_RTOL * scale + 1e-6).all()), what
+
+
+# ---------------- CUB-free onesweep radix sort -----------------------------------------------------------
+@pytest.mark.parametrize("n,bits", [(0, 32), (1, 32), (33, 32), (4096, 32), (4097, 13), (123457, 20), (1 << 20, 32), (3_000_001, 13)])
+def test_onesweep_sort_matches_stable_sort(R, dev, n, bits):
+    g = torch.Generator(device="cpu").manual_seed(n + bits)
+    k = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int32).to(dev)
+    if bits < 32:
+        k = k & ((1 << bits) - 1)
+    v = torch.arange(n, device=dev, dtype=torch.int32)
+    sk, sv = R.sort_pairs_u32(k, v, 0, bits)
+    rk, ri = torch.sort(k.to(torch.int64), stable=True)
+    assert torch.equal(sk.to(torch.int64), rk) and torch.equal(sv.to(torch.int64), ri)
+
+
+def test_onesweep_sort_high_bit_keys_and_ties(R, dev):
+    # unsigned ordering (bit 31 set) and heavy ties -> stability
+    k = torch.tensor([-1, 5, -2147483648, 5, 0, -1, 5], dtype=torch.int32, device=dev)
+    v = torch.arange(7, device=dev, dtype=torch.int32)
+    sk, sv = R.sort_pairs_u32(k, v)
+    ku = k.cpu().numpy().view(np.uint32).astype(np.int64)
+    order = np.argsort(ku, kind="stable")
+    assert list(sv.cpu().numpy()) == list(order)
+    n = 50000
+    k = torch.randint(0, 7, (n,), dtype=torch.int32, device=dev)
+    sk, sv = R.sort_pairs_u32(k, torch.arange(n, device=dev, dtype=torch.int32), 0, 3)
+    rk, ri = torch.sort(k.to(torch.int64), stable=True)
+    assert torch.equal(sv.to(torch.int64), ri)
+
+
+# ---------------- forward + backward parity vs the oracle ----------------------------------------------
+CASES = [
+    # kind, N, deg, W, H, elev, azim, bg
+    ("D0", 2000, 0, 128, 128, 0, 0, (0, 0, 0)),          # BASELINE config 0
+    ("D1", 2000, 3, 128, 128, 10, 30, (0, 0, 0)),
+    ("D1", 1500, 1, 100, 70, -20, 200, (1, 1, 1)),       # ragged: sizes not multiples of 16, white background
+    ("D1", 20000, 2, 200, 120, 5, 75, (0.2, 0.3, 0.4)),
+    ("D0", 30000, 3, 320, 180, 0, 45, (0, 0, 0)),
+]
+
+
+@pytest.mark.parametrize("kind,N,deg,W,H,el,az,bg", CASES)
+def test_forward_backward_parity(R, dev, kind, N, deg, W, H, el, az, bg):
+    cl = O.make_cloud(kind, N, deg, seed=N % 7)
+    st = O.minicam_settings(O.orbit_camera(el, az, 1.75), W, H, 49.1, bg=bg, sh_degree=deg)
+    dc, dd, da = _upstream(H, W, N)
+    out, grads = O.rasterize_with_grads({k: cl[k] for k in NAMES}, st, dc, dd, da)
+    aux = out["aux"]
+    rs = _rs(R, st, dev, deg, debug=True)
+    fs = R.forward_with_state(rs, cl["means3D"].to(dev), cl["opacities"].to(dev), shs=cl["shs"].to(dev),
+                              scales=cl["scales"].to(dev), rotations=cl["rotations"].to(dev))
+    # integer outputs: bit-exact
+    assert torch.equal(fs["radii"].cpu(), out["radii"])
+    assert fs["num_rendered"] == aux["keys"].size
+    assert np.array_equal(fs["sorted_keys"].cpu().numpy().astype(np.uint64), aux["keys"])
+    assert np.array_equal(fs["point_list"].cpu().numpy().astype(np.uint32), aux["point_list"])
+    assert np.array_equal(fs["ranges"].cpu().numpy().astype(np.uint32), aux["ranges"])
+    assert int((fs["n_contrib"].cpu() != aux["n_contrib"]).sum()) == 0
+    # floating outputs
+    assert float((fs["color"].cpu() - out["color"]).abs().max()) < RGBA_ATOL
+    assert float((fs["alpha"].cpu() - out["alpha"]).abs().max()) < RGBA_ATOL
+    assert float((fs["depth"].cpu() - out["depth"]).abs().max()) < RGBA_ATOL * 2
+    assert float((fs["final_T"].cpu() - aux["final_T"]).abs().max()) < RGBA_ATOL
+    # gradients through the reference-facing interface
+    inp = {k: cl[k].to(dev).requires_grad_(True) for k in NAMES}
+    m2 = torch.zeros(N, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = R.GaussianRasterizer(_rs(R, st, dev, deg))(
+        means3D=inp["means3D"], means2D=m2, shs=inp["shs"], colors_precomp=None, opacities=inp["opacities"],
+        scales=inp["scales"], rotations=inp["rotations"], cov3D_precomp=None)
+    ((color * dc.to(dev)).sum() + (depth * dd.to(dev)).sum() + (alpha * da.to(dev)).sum()).backward()
+    for k in NAMES:
+        _grad_close(inp[k].grad, grads[k], f"{kind} N={N} grad {k}")
+    _grad_close(m2.grad, grads["means2D"], "grad means2D")
+    assert float(m2.grad[:, 2].abs().max()) == 0.0
+
+
+def test_golden_fixture_config0(R, dev):
+    g = np.load(os.path.join(GOLDEN, "oracle_config0.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    st = O.minicam_settings(O.orbit_camera(0, 0, 1.75), 128, 128, 49.1, sh_degree=0)
+    rs = _rs(R, st, dev, 0)
+    inp = {k: t(k).requires_grad_(True) for k in NAMES}
+    m2 = torch.zeros(2000, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = R.GaussianRasterizer(rs)(
+        means3D=inp["means3D"], means2D=m2, shs=inp["shs"], colors_precomp=None, opacities=inp["opacities"],
+        scales=inp["scales"], rotations=inp["rotations"], cov3D_precomp=None)
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.abs(color.detach().cpu().numpy() - g["color"]).max() < RGBA_ATOL
+    assert np.abs(alpha.detach().cpu().numpy() - g["alpha"]).max() < RGBA_ATOL
+    ((color * t("dL_dcolor")).sum() + (depth * t("dL_ddepth")).sum() + (alpha * t("dL_dalpha")).sum()).backward()
+    for k in NAMES:
+        _grad_close(inp[k].grad, torch.from_numpy(g["g_" + k]), f"golden grad {k}")
+    fs = R.forward_with_state(rs, t("means3D"), t("opacities"), shs=t("shs"), scales=t("scales"), rotations=t("rotations"))
+    assert np.array_equal(fs["sorted_keys"].cpu().numpy().astype(np.uint64), g["keys"])
+    assert np.array_equal(fs["point_list"].cpu().numpy().astype(np.uint32), g["point_list"])
+    assert np.array_equal(fs["ranges"].cpu().numpy().astype(np.uint32), g["ranges"])
+
+
+def test_colors_precomp_and_cov3d_precomp_paths(R, dev):
+    N, W, H = 3000, 96, 80
+    cl = O.make_cloud("D1", N, 0, seed=9)
+    st = O.minicam_settings(O.orbit_camera(15, -50, 1.75), W, H, 49.1, bg=(0.5, 0.5, 0.5), scale_modifier=1.2)
+    cols = torch.rand(N, 3, generator=torch.Generator().manual_seed(3))
+    cov = O.cov3d_from_scale_rot(cl["scales"], cl["rotations"], 1.2)
+    dc, dd, da = _upstream(H, W, 5)
+    ins = dict(means3D=cl["means3D"], colors_precomp=cols, opacities=cl["opacities"], cov3D_precomp=cov)
+    out, grads = O.rasterize_with_grads(ins, st, dc, dd, da)
+    inp = {k: v.to(dev).requires_grad_(True) for k, v in ins.items()}
+    m2 = torch.zeros(N, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = R.GaussianRasterizer(_rs(R, st, dev, 0))(
+        means3D=inp["means3D"], means2D=m2, shs=None, colors_precomp=inp["colors_precomp"], opacities=inp["opacities"],
+        scales=None, rotations=None, cov3D_precomp=inp["cov3D_precomp"])
+    assert torch.equal(radii.cpu(), out["radii"])
+    assert float((color.detach().cpu() - out["color"]).abs().max()) < RGBA_ATOL
+    ((color * dc.to(dev)).sum() + (depth * dd.to(dev)).sum() + (alpha * da.to(dev)).sum()).backward()
+    for k in ins:
+        _grad_close(inp[k].grad, grads[k], f"precomp grad {k}")
+
+
+def test_empty_culled_and_offscreen_inputs(R, dev):
+    st = O.minicam_settings(O.orbit_camera(0, 0, 1.75), 64, 48, 49.1, bg=(0.1, 0.2, 0.3))
+    rs = _rs(R, st, dev, 0)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    color, radii, depth, alpha = R.GaussianRasterizer(rs)(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1),
+                                                         colors_precomp=z(0, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert radii.numel() == 0 and float(alpha.abs().max()) == 0
+    assert torch.allclose(color[:, 3, 4].cpu(), torch.tensor([0.1, 0.2, 0.3]))
+    # all behind the camera / far off-screen: nothing rendered, zero gradients, no crash
+    m = torch.tensor([[0, 0, 5.0], [0, 0, 1.75 - 0.1], [50.0, 0, 0]], device=dev, requires_grad=True)
+    rot = torch.tensor([[1.0, 0, 0, 0]], device=dev).repeat(3, 1)
+    color, radii, depth, alpha = R.GaussianRasterizer(rs)(means3D=m, means2D=z(3, 3), opacities=torch.full((3, 1), 0.5, device=dev),
+                                                         colors_precomp=torch.ones(3, 3, device=dev),
+                                                         scales=torch.full((3, 3), 0.01, device=dev), rotations=rot)
+    assert int(radii.abs().sum()) == 0 and float(alpha.abs().max()) == 0
+    color.sum().backward()
+    assert float(m.grad.abs().max()) == 0
+
+
+def test_inference_mode_and_reference_render_wrapper_contract(R, dev):
+    """Render-only node path (nodes.py:1130-1163 runs under inference_mode) + the dict built at main_3DGS_renderer.py:942-949."""
+    cl = O.make_cloud("D1", 4000, 1, seed=1)
+    st = O.minicam_settings(O.orbit_camera(-10, 120, 1.75), 160, 96, 49.1, sh_degree=1)
+    rs = _rs(R, st, dev, 1)
+    ref, _, _, refa = O.rasterize(cl["means3D"], None, cl["shs"], None, cl["opacities"], cl["scales"], cl["rotations"], None, st)
+    with torch.inference_mode():
+        img, radii, depth, alpha = R.GaussianRasterizer(raster_settings=rs)(
+            means3D=cl["means3D"].to(dev), means2D=torch.zeros(4000, 3, device=dev), shs=cl["shs"].to(dev),
+            colors_precomp=None, opacities=cl["opacities"].to(dev), scales=cl["scales"].to(dev),
+            rotations=cl["rotations"].to(dev), cov3D_precomp=None)
+        img = img.clamp(0, 1)
+        vis = radii > 0
+    assert img.shape == (3, 96, 160) and depth.shape == (1, 96, 160) and alpha.shape == (1, 96, 160)
+    assert radii.dtype == torch.int32 and vis.dtype == torch.bool
+    assert float((img.cpu() - ref.clamp(0, 1)).abs().max()) < RGBA_ATOL
+    assert float((alpha.cpu() - refa).abs().max()) < RGBA_ATOL
+
+
+def test_knn_mean_dist2_matches_kdtree(R, dev):
+    pts = O.make_cloud("D0", 5000, 0, seed=2)["means3D"]
+    got = R.knn_mean_dist2(pts.to(dev)).cpu().numpy()
+    ref = O.knn_mean_dist2(pts.numpy())
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-9)
+
+
+# ---------------- multi-view step entries ---------------------------------------------------------------
+def test_multiview_step_entries_agree_with_per_view_path(dev):
+    from gs_b200 import camera, optim_step, synthetic
+    N, V, W, H, deg = 20000, 5, 256, 144, 2
+    cloud = synthetic.make_cloud("D1", N, deg, seed=5, device=dev)
+    params = optim_step.PackedParams(cloud)
+    vnp = camera.orbit_views(V, W, H)
+    views = optim_step.ViewSet(vnp, W, H, deg, dev)
+    dl_cpu = torch.rand(V, 5, H, W, generator=torch.Generator().manual_seed(7)) * 2 - 1
+    dl = dl_cpu.to(dev)
+    ia = torch.empty(V, 5, H, W, device=dev); ib = torch.empty(V, 5, H, W, device=dev)
+    p1 = optim_step.step_device(params, views, dl, ia); g1 = params.grads.clone()
+    for _ in range(3):
+        p2 = optim_step.step_device_pipelined(params, views, dl, ib); g2 = params.grads.clone()
+        assert p1 == p2 and torch.equal(ia, ib)
+        assert float((g1 - g2).norm() / g1.norm()) < 1e-5          # atomics: summation order differs
+    hs = optim_step.HostStep({k: v.cpu() for k, v in cloud.items()}, vnp, W, H, deg, dl_cpu)
+    for _ in range(2):
+        assert hs.run() == p1
+        assert float((hs.grads.to(dev) - g1).norm() / g1.norm()) < 1e-5
+    # and the packed buffer equals the sum of per-view oracle-checked autograd gradients for one view
+    from gs_b200 import rasterizer as R
+    cam = camera.MiniCam(camera.orbit_camera(0, 0.0, 1.75), W, H, np.deg2rad(49.1),
+                         2 * np.arctan(np.tan(np.deg2rad(49.1) / 2) * W / H), 0.01, 100.0, device=dev)
+    assert np.allclose(vnp[0, :16], cam.world_view_transform.reshape(-1).cpu().numpy(), atol=1e-6)
+
+
+# ---------------- full-size properties (BASELINE config 1: 1M Gaussians, 1080p) -----------------------
+def test_full_size_properties_config1(dev):
+    from gs_b200 import camera, optim_step, synthetic
+    from gs_b200 import rasterizer as R
+    N, W, H, deg = 1_000_000, 1920, 1080, 3
+    cloud = synthetic.make_cloud("D0", N, deg, seed=0, device=dev)
+    vnp = camera.orbit_views(1, W, H)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    rs = R.GaussianRasterizationSettings(H, W, float(vnp[0, 38]), float(vnp[0, 39]), t(vnp[0, 35:38].copy()), 1.0,
+                                        t(vnp[0, :16].copy()).view(4, 4), t(vnp[0, 16:32].copy()).view(4, 4), deg,
+                                        t(vnp[0, 32:35].copy()), False, False)
+    fs = R.forward_with_state(rs, cloud["means3D"], cloud["opacities"], shs=cloud["shs"], scales=cloud["scales"],
+                              rotations=cloud["rotations"])
+    P = fs["num_rendered"]
+    assert P > N                                                   # K > 1 pairs per Gaussian at this density
+    keys = fs["sorted_keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                     # sortedness of the 64-bit keys
+    # equal keys keep Gaussian-index order (stability)
+    eq = keys[1:] == keys[:-1]
+    pl = fs["point_list"].to(torch.int64)
+    assert bool((pl[1:][eq] > pl[:-1][eq]).all())
+    r = fs["ranges"].to(torch.int64)
+    assert int((r[:, 1] - r[:, 0]).sum()) == P                    # ranges partition the list
+    tiles = (keys >> 32)
+    nz = r[:, 1] > r[:, 0]
+    assert bool((tiles[r[nz, 0]] == torch.nonzero(nz).squeeze(1)).all())
+    # every Gaussian's pair count equals its rect area: histogram of point_list == tiles implied by radii>0
+    cnt = torch.bincount(pl, minlength=N)
+    assert bool(((cnt > 0) == (fs["radii"] > 0)).all())
+    # transmittance bookkeeping and bounds
+    assert float((fs["alpha"][0] + fs["final_T"] - 1).abs().max()) < 1e-4
+    assert bool((fs["n_contrib"].to(torch.int64) <= (r[:, 1] - r[:, 0]).max()).all())
+    assert float(fs["color"].min()) >= 0 and bool(torch.isfinite(fs["color"]).all())
+    # permutation invariance: shuffling the Gaussians leaves the image unchanged (depth ties aside)
+    perm = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    fs2 = R.forward_with_state(rs, cloud["means3D"][perm].contiguous(), cloud["opacities"][perm].contiguous(),
+                               shs=cloud["shs"][perm].contiguous(), scales=cloud["scales"][perm].contiguous(),
+                               rotations=cloud["rotations"][perm].contiguous())
+    assert fs2["num_rendered"] == P
+    assert float((fs2["color"] - fs["color"]).abs().max()) < 1e-4
+    # backward is linear in the upstream gradient: grads(2 dL) == 2 grads(dL)
+    params = optim_step.PackedParams(cloud)
+    views = optim_step.ViewSet(vnp, W, H, deg, dev)
+    dl = (torch.rand(1, 5, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 2 - 1)
+    optim_step.step_device_pipelined(params, views, dl); g1 = params.grads.clone()
+    optim_step.step_device_pipelined(params, views, 2 * dl); g2 = params.grads.clone()
+    assert bool(torch.isfinite(g1).all())
+    assert float((g2 - 2 * g1).norm() / (2 * g1).norm()) < 1e-5
