@@ -7,6 +7,7 @@
 
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -200,10 +201,14 @@ struct FwdCtx {
     FwdCtx(gs_b200_alloc_fn fn, void* user, cudaStream_t st) : A{fn, user, st}, s(st) {}
 };
 
+// per-view arrays already produced by the multi-view preprocess (gs_launch_preprocess_multi)
+struct PreView { SplatRec* recs; uint32_t *tiles, *dkeys, *ids, *min_key; };
+
 static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
                        const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
                        const float* rotations, const float* cov3D_precomp, float* out_color, float* out_depth,
-                       float* out_alpha, int32_t* radii, gs_b200_state* state, unsigned long long* host_total) {
+                       float* out_alpha, int32_t* radii, gs_b200_state* state, unsigned long long* host_total,
+                       const PreView* pre = nullptr) {
     cudaStream_t s = c.s;
     if (make_view_args(view, c.va)) return 1;
     if (check_inputs(N, M, view->sh_degree, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)) return 1;
@@ -226,7 +231,8 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
     state->final_T = ci.take<float>(npix);
     GS_CUDA_CHECK(cudaMemsetAsync(state->ranges, 0, (size_t)ntiles * 2 * 4, s));
 
-    c.recs = (SplatRec*)A.get(GS_B200_BUF_GEOM, (size_t)N * sizeof(SplatRec), &state->owned[GS_B200_BUF_GEOM]);
+    if (pre) c.recs = pre->recs;
+    else c.recs = (SplatRec*)A.get(GS_B200_BUF_GEOM, (size_t)N * sizeof(SplatRec), &state->owned[GS_B200_BUF_GEOM]);
     if (A.failed) return 1;
     state->geom = c.recs;
     *host_total = 0;
@@ -239,6 +245,7 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
         uint32_t* tiles = cv.take<uint32_t>(N);
         uint32_t* dkeys = cv.take<uint32_t>(N);
         uint32_t* ids = cv.take<uint32_t>(N);
+        if (pre) { tiles = pre->tiles; dkeys = pre->dkeys; ids = pre->ids; }
         uint32_t* dkeys_alt = cv.take<uint32_t>(N);
         uint32_t* ids_alt = cv.take<uint32_t>(N);
         c.offsets = cv.take<uint32_t>(N);
@@ -444,6 +451,7 @@ struct StepCache {
     cudaEvent_t evFork = nullptr, evPB = nullptr;
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
+    Region ws_recs, ws_sg, ws_u32;               // per-chunk [VB][N] arrays of the multi-view step
     int ensure_init() {
         if (init) return 0;
         for (int i = 0; i < 2; i++) {
@@ -470,6 +478,10 @@ PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
 }
 
 // Device-resident core.  views_host gives tanfov per view (host side), views_dev the matrices.
+// Views are handled in chunks of <= VB: ONE multi-view preprocess pass over the Gaussians for the chunk
+// (parameters read once), then per view [depth sort -> scan -> (host: pair count) -> emit -> tile sort ->
+// ranges -> composite fwd -> composite bwd] pipelined over the two slot streams, then ONE multi-view
+// preprocess-backward pass (parameters read once, gradients written once).
 int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const float* views_host,
               const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
               const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
@@ -477,9 +489,19 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     StepCache& C = g_step;
     if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
-    // fork: both slot streams start after everything already queued on the caller's stream
-    GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
-    for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evFork, 0));
+    const int VB = std::min(V, std::min(gs_preprocess_multi_max_views(), 16));
+    // chunk workspace: [VB][N] arrays
+    const size_t nvb = (size_t)VB * N;
+    if (Slot::ensure(C.ws_recs, nvb * sizeof(SplatRec), user) || Slot::ensure(C.ws_sg, nvb * sizeof(SplatGrad), user) ||
+        Slot::ensure(C.ws_u32, nvb * 4 * 4 + 256 * 4, user)) return 1;
+    SplatRec* recs_all = (SplatRec*)C.ws_recs.p;
+    SplatGrad* sg_all = (SplatGrad*)C.ws_sg.p;
+    uint32_t* u32 = (uint32_t*)C.ws_u32.p;
+    int32_t* radii_all = (int32_t*)u32;
+    uint32_t* tiles_all = u32 + nvb;
+    uint32_t* dkeys_all = u32 + 2 * nvb;
+    uint32_t* ids_all = u32 + 3 * nvb;
+    uint32_t* minkeys = u32 + 4 * nvb;          // [VB] stride 2 words
 
     gs_b200_state st[2];
     gs_b200_view view[2];
@@ -487,60 +509,69 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     int64_t rendered = 0;
     int rc = 0;
 
-    auto launch_a = [&](int v) -> int {
-        Slot& S = C.slot[v & 1];
-        S.begin_call();
-        if (Slot::ensure(S.radii, (size_t)N * 4, S.stream) || Slot::ensure(S.sgrad, (size_t)N * sizeof(SplatGrad), S.stream) ||
-            (!images_dev && Slot::ensure(S.image, 5 * npix * 4, S.stream))) return 1;
-        const float* vh = views_host + (size_t)v * 40;
-        const float* vd = views_dev + (size_t)v * 40;
-        gs_b200_view& vw = view[v & 1];
-        vw.image_height = H; vw.image_width = W; vw.tanfovx = vh[38]; vw.tanfovy = vh[39];
-        vw.bg = vd + 35; vw.scale_modifier = scale_modifier; vw.viewmatrix = vd; vw.projmatrix = vd + 16;
-        vw.sh_degree = sh_degree; vw.campos = vd + 32; vw.prefiltered = 0; vw.debug = 0;
-        float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
-        delete ctx[v & 1];
-        ctx[v & 1] = new FwdCtx(slot_alloc_cb, &S, S.stream);
-        if (fwd_phase_a(*ctx[v & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
-                        img, img + 3 * npix, img + 4 * npix, (int32_t*)S.radii.p, &st[v & 1], S.host_total)) return 1;
-        GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
-        return S.failed ? 1 : 0;
-    };
+    for (int v0 = 0; v0 < V && !rc; v0 += VB) {
+        const int nv = std::min(VB, V - v0);
+        GS_CUDA_CHECK(cudaMemsetAsync(sg_all, 0, (size_t)nv * N * sizeof(SplatGrad), user));
+        GS_CUDA_CHECK(cudaMemsetAsync(minkeys, 0xFF, 256 * 4, user));
+        { StageTimer t(0, user);
+        if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
+                                       par.shs, par.opac, par.scales, par.rots, recs_all, radii_all, tiles_all,
+                                       dkeys_all, ids_all, minkeys, user)) return 1; }
+        // fork: both slot streams continue after the preprocess
+        GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
+        for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evFork, 0));
 
-    rc = launch_a(0);
-    for (int v = 0; v < V && !rc; v++) {
-        Slot& S = C.slot[v & 1];
-        if (v + 1 < V) { rc = launch_a(v + 1); if (rc) break; }
-        GS_CUDA_CHECK(cudaEventSynchronize(S.evA));
-        if ((rc = fwd_phase_b(*ctx[v & 1]))) break;
-        rendered += st[v & 1].num_rendered;
-        // ---- backward of view v on the same stream
-        SplatGrad* sg = (SplatGrad*)S.sgrad.p;
-        GS_CUDA_CHECK(cudaMemsetAsync(sg, 0, (size_t)N * sizeof(SplatGrad), S.stream));
-        const float* up = dL_dout_dev + (size_t)v * 5 * npix;
-        if (up_ready) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, up_ready[v], 0));
-        if (st[v & 1].num_rendered > 0) {
-            StageTimer t(7, S.stream);
-            if ((rc = gs_launch_render_backward(ctx[v & 1]->va, (const SplatRec*)st[v & 1].geom, st[v & 1].point_list,
-                                                st[v & 1].ranges, st[v & 1].n_contrib, st[v & 1].final_T, up,
-                                                up + 3 * npix, up + 4 * npix, sg, S.stream))) break;
+        auto launch_a = [&](int j) -> int {          // j: view index inside the chunk
+            Slot& S = C.slot[j & 1];
+            S.begin_call();
+            if (!images_dev && Slot::ensure(S.image, 5 * npix * 4, S.stream)) return 1;
+            const int v = v0 + j;
+            const float* vh = views_host + (size_t)v * 40;
+            const float* vd = views_dev + (size_t)v * 40;
+            gs_b200_view& vw = view[j & 1];
+            vw.image_height = H; vw.image_width = W; vw.tanfovx = vh[38]; vw.tanfovy = vh[39];
+            vw.bg = vd + 35; vw.scale_modifier = scale_modifier; vw.viewmatrix = vd; vw.projmatrix = vd + 16;
+            vw.sh_degree = sh_degree; vw.campos = vd + 32; vw.prefiltered = 0; vw.debug = 0;
+            float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
+            delete ctx[j & 1];
+            ctx[j & 1] = new FwdCtx(slot_alloc_cb, &S, S.stream);
+            const size_t o = (size_t)j * N;
+            PreView pre{recs_all + o, tiles_all + o, dkeys_all + o, ids_all + o, minkeys + 2 * j};
+            if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
+                            img, img + 3 * npix, img + 4 * npix, radii_all + o, &st[j & 1], S.host_total, &pre)) return 1;
+            GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
+            return S.failed ? 1 : 0;
+        };
+
+        rc = launch_a(0);
+        for (int j = 0; j < nv && !rc; j++) {
+            Slot& S = C.slot[j & 1];
+            if (j + 1 < nv) { rc = launch_a(j + 1); if (rc) break; }
+            GS_CUDA_CHECK(cudaEventSynchronize(S.evA));
+            if ((rc = fwd_phase_b(*ctx[j & 1]))) break;
+            rendered += st[j & 1].num_rendered;
+            const int v = v0 + j;
+            const float* up = dL_dout_dev + (size_t)v * 5 * npix;
+            if (up_ready) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, up_ready[v], 0));
+            if (st[j & 1].num_rendered > 0) {
+                StageTimer t(7, S.stream);
+                if ((rc = gs_launch_render_backward(ctx[j & 1]->va, (const SplatRec*)st[j & 1].geom, st[j & 1].point_list,
+                                                    st[j & 1].ranges, st[j & 1].n_contrib, st[j & 1].final_T, up,
+                                                    up + 3 * npix, up + 4 * npix, sg_all + (size_t)j * N, S.stream))) break;
+            }
+            if (S.failed) { rc = 1; break; }
         }
-        // gradient accumulation into the shared packed buffer is ordered view by view
-        if (v > 0) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, C.evPB, 0));
-        {
-            StageTimer t(8, S.stream);
-            if ((rc = gs_launch_preprocess_backward(ctx[v & 1]->va, N, M, par.means, par.shs, nullptr, par.opac, par.scales,
-                                                    par.rots, nullptr, (const int32_t*)S.radii.p, sg, grd.means, grd.m2d,
-                                                    grd.shs, nullptr, grd.opac, grd.scales, grd.rots, nullptr, 1, S.stream))) break;
+        for (int i = 0; i < 2; i++) { delete ctx[i]; ctx[i] = nullptr; }
+        // join: the caller's stream continues after both slot streams
+        for (int i = 0; i < 2; i++) {
+            cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
+            cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
         }
-        GS_CUDA_CHECK(cudaEventRecord(C.evPB, S.stream));
-        if (S.failed) { rc = 1; break; }
-    }
-    for (int i = 0; i < 2; i++) { delete ctx[i]; ctx[i] = nullptr; }
-    // join: the caller's stream continues after both slot streams
-    for (int i = 0; i < 2; i++) {
-        cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
-        cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
+        if (rc) break;
+        { StageTimer t(8, user);
+        rc = gs_launch_preprocess_backward_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M,
+                                                 par.means, par.shs, par.scales, par.rots, radii_all, sg_all, grd.means,
+                                                 grd.m2d, grd.shs, grd.opac, grd.scales, grd.rots, v0 > 0 ? 1 : 0, user); }
     }
     if (num_rendered_out) *num_rendered_out = rendered;
     return rc;

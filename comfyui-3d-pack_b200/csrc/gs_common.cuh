@@ -147,6 +147,18 @@ int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float*
                                   float* dcolors, float* dopac, float* dscales, float* drots, float* dcov3D,
                                   int accumulate, cudaStream_t s);
 
+int gs_preprocess_multi_max_views();
+int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int sh_degree, float scale_modifier, int N,
+                               int M, const float* means3D, const float* shs, const float* opacities,
+                               const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
+                               uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
+                               cudaStream_t s);
+int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, int H, int sh_degree,
+                                        float scale_modifier, int N, int M, const float* means3D, const float* shs,
+                                        const float* scales, const float* rotations, const int32_t* radii,
+                                        const SplatGrad* sg, float* dmeans3D, float* dmeans2D, float* dshs,
+                                        float* dopac, float* dscales, float* drots, int accumulate, cudaStream_t s);
+
 size_t gs_sort_scratch_bytes(int64_t n);
 int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
                       int begin_bit, int end_bit, void* scratch, int* result_in_alt, cudaStream_t s);

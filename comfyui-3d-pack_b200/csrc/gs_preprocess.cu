@@ -54,10 +54,107 @@ __device__ __forceinline__ void sh_to_rgb(int deg, int M, const float* __restric
 
 constexpr int PP_THREADS = 128;
 
-// One thread per Gaussian.  SH coefficients of the CTA's 128 Gaussians are one
-// contiguous span of global memory (128*M*12 B): it is staged into shared
-// memory with fully coalesced 128-bit loads, then each thread reads its own
-// row (row stride padded to an odd word count -> bank-conflict free).
+struct ViewK {                      // per-view constants, matrices in shared memory
+    const float* m; const float* p; const float* cam;
+    float tanfovx, tanfovy, fx, fy;
+    int W, H, tiles_x, tiles_y;
+};
+
+// Sigma = R diag(s^2) R^T packed [xx,xy,xz,yy,yz,zz]; order of operations is part of the bit-exactness contract.
+__device__ __forceinline__ void cov3d_of(const float* __restrict__ scales, const float* __restrict__ rotations,
+                                         const float* __restrict__ cov3D_precomp, float mod, int idx, float c[6]) {
+    if (cov3D_precomp != nullptr) {
+        const float* cp = cov3D_precomp + 6 * (size_t)idx;
+#pragma unroll
+        for (int k = 0; k < 6; k++) c[k] = cp[k];
+        return;
+    }
+    const float s0 = mod * scales[3 * idx + 0], s1 = mod * scales[3 * idx + 1], s2 = mod * scales[3 * idx + 2];
+    const float* q = rotations + 4 * (size_t)idx;
+    const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
+    const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz), R01 = 2.0f * (qx * qy - r * qz), R02 = 2.0f * (qx * qz + r * qy);
+    const float R10 = 2.0f * (qx * qy + r * qz), R11 = 1.0f - 2.0f * (qx * qx + qz * qz), R12 = 2.0f * (qy * qz - r * qx);
+    const float R20 = 2.0f * (qx * qz - r * qy), R21 = 2.0f * (qy * qz + r * qx), R22 = 1.0f - 2.0f * (qx * qx + qy * qy);
+    const float M00 = R00 * s0, M01 = R01 * s1, M02 = R02 * s2;
+    const float M10 = R10 * s0, M11 = R11 * s1, M12 = R12 * s2;
+    const float M20 = R20 * s0, M21 = R21 * s1, M22 = R22 * s2;
+    c[0] = M00 * M00 + M01 * M01 + M02 * M02;
+    c[1] = M00 * M10 + M01 * M11 + M02 * M12;
+    c[2] = M00 * M20 + M01 * M21 + M02 * M22;
+    c[3] = M10 * M10 + M11 * M11 + M12 * M12;
+    c[4] = M10 * M20 + M11 * M21 + M12 * M22;
+    c[5] = M20 * M20 + M21 * M21 + M22 * M22;
+}
+
+// View-dependent part for one Gaussian: cull, project, EWA cov2D, extent, rect, colour -> record.
+__device__ __forceinline__ void project_view(const ViewK& vk, int deg, int M, float x, float y, float z,
+                                             const float c[6], float opacity, const float* __restrict__ sh_row,
+                                             const float* __restrict__ col, SplatRec& rec, int& my_radius,
+                                             uint32_t& tiles, uint32_t& dkey) {
+    const float* m = vk.m;
+    const float* p = vk.p;
+    rec.g = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec.k = make_float4(0.f, 0.f, 0.f, 0.f);
+    my_radius = 0; tiles = 0; dkey = 0xFFFFFFFFu;
+    const float tx = m[0] * x + m[4] * y + m[8] * z + m[12];
+    const float ty = m[1] * x + m[5] * y + m[9] * z + m[13];
+    const float tz = m[2] * x + m[6] * y + m[10] * z + m[14];
+    if (!(tz > 0.2f)) return;
+    const float hx = p[0] * x + p[4] * y + p[8] * z + p[12];
+    const float hy = p[1] * x + p[5] * y + p[9] * z + p[13];
+    const float hw = p[3] * x + p[7] * y + p[11] * z + p[15];
+    const float pw = 1.0f / (hw + 0.0000001f);
+    const float ndcx = hx * pw, ndcy = hy * pw;
+    const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
+    const float fx = vk.fx, fy = vk.fy;
+    const float limx = 1.3f * vk.tanfovx, limy = 1.3f * vk.tanfovy;
+    const float txtz = tx / tz, tytz = ty / tz;
+    const float cx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    const float cy = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float J00 = fx / tz, J02 = -(fx * cx) / (tz * tz);
+    const float J11 = fy / tz, J12 = -(fy * cy) / (tz * tz);
+    const float T00 = J00 * m[0] + J02 * m[2], T01 = J00 * m[4] + J02 * m[6], T02 = J00 * m[8] + J02 * m[10];
+    const float T10 = J11 * m[1] + J12 * m[2], T11 = J11 * m[5] + J12 * m[6], T12 = J11 * m[9] + J12 * m[10];
+    const float v00 = c0 * T00 + c1 * T01 + c2 * T02;
+    const float v01 = c1 * T00 + c3 * T01 + c4 * T02;
+    const float v02 = c2 * T00 + c4 * T01 + c5 * T02;
+    const float v10 = c0 * T10 + c1 * T11 + c2 * T12;
+    const float v11 = c1 * T10 + c3 * T11 + c4 * T12;
+    const float v12 = c2 * T10 + c4 * T11 + c5 * T12;
+    const float ca = T00 * v00 + T01 * v01 + T02 * v02 + 0.3f;
+    const float cb = T00 * v10 + T01 * v11 + T02 * v12;
+    const float cc = T10 * v10 + T11 * v11 + T12 * v12 + 0.3f;
+    const float det = ca * cc - cb * cb;
+    if (det == 0.0f) return;
+    const float det_inv = 1.0f / det;
+    const float mid = 0.5f * (ca + cc);
+    const float disc = sqrtf(fmaxf(mid * mid - det, 0.1f));
+    const float lam1 = mid + disc, lam2 = mid - disc;
+    const float radf = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
+    const float px = ((ndcx + 1.0f) * (float)vk.W - 1.0f) * 0.5f;
+    const float py = ((ndcy + 1.0f) * (float)vk.H - 1.0f) * 0.5f;
+    const int rad_i = (int)radf;
+    int x0, y0, x1, y1;
+    get_rect(px, py, rad_i, vk.tiles_x, vk.tiles_y, x0, y0, x1, y1);
+    const int area = (x1 - x0) * (y1 - y0);
+    if (area <= 0) return;
+    my_radius = rad_i;
+    tiles = (uint32_t)area;
+    dkey = __float_as_uint(tz);
+    float cr, cg, cbl;
+    if (col != nullptr) { cr = col[0]; cg = col[1]; cbl = col[2]; }
+    else sh_to_rgb(deg, M, sh_row, x - vk.cam[0], y - vk.cam[1], z - vk.cam[2], cr, cg, cbl);
+    rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
+    // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
+    const float L2E = 1.4426950408889634f;
+    rec.c = make_float4(-0.5f * L2E * (cc * det_inv), L2E * (cb * det_inv), -0.5f * L2E * (ca * det_inv), opacity);
+    rec.k = make_float4(cr, cg, cbl, __uint_as_float(tiles));
+}
+
+// One thread per Gaussian.  SH coefficients of the CTA's 128 Gaussians are one contiguous span of global
+// memory (128*M*12 B): staged into shared memory with coalesced 128-bit loads, then each thread reads its
+// own row (row stride padded to an odd word count -> bank-conflict free).
 __global__ void __launch_bounds__(PP_THREADS)
 preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                   const float* __restrict__ colors_precomp, const float* __restrict__ opacities,
@@ -73,7 +170,6 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
     if (tid == 0) s_min = 0xFFFFFFFFu;
     if (tid < 16) { s_view[tid] = __ldg(va.view + tid); s_proj[tid] = __ldg(va.proj + tid); }
     if (tid < 3) s_cam[tid] = __ldg(va.campos + tid);
-
     const int row = 3 * M;
     const int rowp = gs_rowp(row);
     if (shs != nullptr)
@@ -82,102 +178,13 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
 
     const bool live = base + tid < N;
     const int idx = live ? base + tid : N - 1;      // tail threads redo the last Gaussian, stores are guarded
-    const float* m = s_view;
-    const float* p = s_proj;
-
     const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
-    const float tx = m[0] * x + m[4] * y + m[8] * z + m[12];
-    const float ty = m[1] * x + m[5] * y + m[9] * z + m[13];
-    const float tz = m[2] * x + m[6] * y + m[10] * z + m[14];
-
-    SplatRec rec;
-    rec.g = make_float4(0.f, 0.f, 0.f, 0.f);
-    rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
-    rec.k = make_float4(0.f, 0.f, 0.f, 0.f);
-    int my_radius = 0;
-    uint32_t tiles = 0;
-    uint32_t dkey = 0xFFFFFFFFu;
-
-    if (tz > 0.2f) {
-        const float hx = p[0] * x + p[4] * y + p[8] * z + p[12];
-        const float hy = p[1] * x + p[5] * y + p[9] * z + p[13];
-        const float hw = p[3] * x + p[7] * y + p[11] * z + p[15];
-        const float pw = 1.0f / (hw + 0.0000001f);
-        const float ndcx = hx * pw, ndcy = hy * pw;
-
-        float c0, c1, c2, c3, c4, c5;
-        if (cov3D_precomp != nullptr) {
-            const float* c = cov3D_precomp + 6 * (size_t)idx;
-            c0 = c[0]; c1 = c[1]; c2 = c[2]; c3 = c[3]; c4 = c[4]; c5 = c[5];
-        } else {
-            const float mod = va.scale_modifier;
-            const float s0 = mod * scales[3 * idx + 0], s1 = mod * scales[3 * idx + 1], s2 = mod * scales[3 * idx + 2];
-            const float* q = rotations + 4 * (size_t)idx;
-            const float r = q[0], qx = q[1], qy = q[2], qz = q[3];
-            const float R00 = 1.0f - 2.0f * (qy * qy + qz * qz), R01 = 2.0f * (qx * qy - r * qz), R02 = 2.0f * (qx * qz + r * qy);
-            const float R10 = 2.0f * (qx * qy + r * qz), R11 = 1.0f - 2.0f * (qx * qx + qz * qz), R12 = 2.0f * (qy * qz - r * qx);
-            const float R20 = 2.0f * (qx * qz - r * qy), R21 = 2.0f * (qy * qz + r * qx), R22 = 1.0f - 2.0f * (qx * qx + qy * qy);
-            const float M00 = R00 * s0, M01 = R01 * s1, M02 = R02 * s2;
-            const float M10 = R10 * s0, M11 = R11 * s1, M12 = R12 * s2;
-            const float M20 = R20 * s0, M21 = R21 * s1, M22 = R22 * s2;
-            c0 = M00 * M00 + M01 * M01 + M02 * M02;
-            c1 = M00 * M10 + M01 * M11 + M02 * M12;
-            c2 = M00 * M20 + M01 * M21 + M02 * M22;
-            c3 = M10 * M10 + M11 * M11 + M12 * M12;
-            c4 = M10 * M20 + M11 * M21 + M12 * M22;
-            c5 = M20 * M20 + M21 * M21 + M22 * M22;
-        }
-
-        const float fx = va.focal_x, fy = va.focal_y;
-        const float limx = 1.3f * va.tanfovx, limy = 1.3f * va.tanfovy;
-        const float txtz = tx / tz, tytz = ty / tz;
-        const float cx = fminf(limx, fmaxf(-limx, txtz)) * tz;
-        const float cy = fminf(limy, fmaxf(-limy, tytz)) * tz;
-        const float J00 = fx / tz, J02 = -(fx * cx) / (tz * tz);
-        const float J11 = fy / tz, J12 = -(fy * cy) / (tz * tz);
-        const float T00 = J00 * m[0] + J02 * m[2], T01 = J00 * m[4] + J02 * m[6], T02 = J00 * m[8] + J02 * m[10];
-        const float T10 = J11 * m[1] + J12 * m[2], T11 = J11 * m[5] + J12 * m[6], T12 = J11 * m[9] + J12 * m[10];
-        const float v00 = c0 * T00 + c1 * T01 + c2 * T02;
-        const float v01 = c1 * T00 + c3 * T01 + c4 * T02;
-        const float v02 = c2 * T00 + c4 * T01 + c5 * T02;
-        const float v10 = c0 * T10 + c1 * T11 + c2 * T12;
-        const float v11 = c1 * T10 + c3 * T11 + c4 * T12;
-        const float v12 = c2 * T10 + c4 * T11 + c5 * T12;
-        const float ca = T00 * v00 + T01 * v01 + T02 * v02 + 0.3f;
-        const float cb = T00 * v10 + T01 * v11 + T02 * v12;
-        const float cc = T10 * v10 + T11 * v11 + T12 * v12 + 0.3f;
-
-        const float det = ca * cc - cb * cb;
-        if (det != 0.0f) {
-            const float det_inv = 1.0f / det;
-            const float mid = 0.5f * (ca + cc);
-            const float disc = sqrtf(fmaxf(mid * mid - det, 0.1f));
-            const float lam1 = mid + disc, lam2 = mid - disc;
-            const float radf = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
-            const float px = ((ndcx + 1.0f) * (float)va.W - 1.0f) * 0.5f;
-            const float py = ((ndcy + 1.0f) * (float)va.H - 1.0f) * 0.5f;
-            int rad_i = (int)radf;
-            int x0, y0, x1, y1;
-            get_rect(px, py, rad_i, va.tiles_x, va.tiles_y, x0, y0, x1, y1);
-            const int area = (x1 - x0) * (y1 - y0);
-            if (area > 0) {
-                my_radius = rad_i;
-                tiles = (uint32_t)area;
-                dkey = __float_as_uint(tz);
-                float cr, cg, cbl;
-                if (colors_precomp != nullptr) {
-                    cr = colors_precomp[3 * idx + 0]; cg = colors_precomp[3 * idx + 1]; cbl = colors_precomp[3 * idx + 2];
-                } else {
-                    sh_to_rgb(va.sh_degree, M, s_sh + (idx - base) * rowp, x - s_cam[0], y - s_cam[1], z - s_cam[2], cr, cg, cbl);
-                }
-                rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
-                // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
-                const float L2E = 1.4426950408889634f;
-                rec.c = make_float4(-0.5f * L2E * (cc * det_inv), L2E * (cb * det_inv), -0.5f * L2E * (ca * det_inv), opacities[idx]);
-                rec.k = make_float4(cr, cg, cbl, __uint_as_float(tiles));
-            }
-        }
-    }
+    float c[6];
+    cov3d_of(scales, rotations, cov3D_precomp, va.scale_modifier, idx, c);
+    ViewK vk{s_view, s_proj, s_cam, va.tanfovx, va.tanfovy, va.focal_x, va.focal_y, va.W, va.H, va.tiles_x, va.tiles_y};
+    SplatRec rec; int my_radius; uint32_t tiles, dkey;
+    project_view(vk, va.sh_degree, M, x, y, z, c, opacities[idx], s_sh + (idx - base) * rowp,
+                 colors_precomp ? colors_precomp + 3 * (size_t)idx : nullptr, rec, my_radius, tiles, dkey);
     if (live) {
         recs[idx] = rec;
         radii[idx] = my_radius;
@@ -189,6 +196,56 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
     // minimum visible depth key of the view -> bias of the depth sort (see gs_sort.cu)
     __syncthreads();
     if (tid == 0 && s_min != 0xFFFFFFFFu) atomicMin(min_key, s_min);
+}
+
+// All V views of a multi-view step in ONE pass over the Gaussians: parameters (236 B each at SH 3) are read
+// once instead of V times, cov3D is computed once; per view only the 64 B of outputs are written.
+// views: V x 40 floats (viewmatrix 16 | projmatrix 16 | campos 3 | bg 3 | tanfovx | tanfovy), outputs [V][N].
+constexpr int PP_MAXV = 16;
+__global__ void __launch_bounds__(PP_THREADS)
+preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, int sh_degree, float scale_modifier,
+                        int N, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                        const float* __restrict__ opacities, const float* __restrict__ scales,
+                        const float* __restrict__ rotations, SplatRec* __restrict__ recs,
+                        int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
+                        uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids,
+                        uint32_t* __restrict__ min_keys /* [V] stride 2 words */) {
+    extern __shared__ __align__(16) float s_sh[];
+    __shared__ float s_views[PP_MAXV * 40];
+    __shared__ uint32_t s_min[PP_MAXV];
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PP_THREADS;
+    for (int i = tid; i < V * 40; i += PP_THREADS) s_views[i] = __ldg(views + i);
+    if (tid < V) s_min[tid] = 0xFFFFFFFFu;
+    const int row = 3 * M;
+    const int rowp = gs_rowp(row);
+    gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
+    __syncthreads();
+    const bool live = base + tid < N;
+    const int idx = live ? base + tid : N - 1;
+    const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const float opacity = opacities[idx];
+    float c[6];
+    cov3d_of(scales, rotations, nullptr, scale_modifier, idx, c);
+    const int tiles_x = (W + GS_TILE - 1) / GS_TILE, tiles_y = (H + GS_TILE - 1) / GS_TILE;
+    for (int v = 0; v < V; v++) {
+        const float* vw = s_views + v * 40;
+        const float tfx = vw[38], tfy = vw[39];
+        ViewK vk{vw, vw + 16, vw + 32, tfx, tfy, (float)W / (2.0f * tfx), (float)H / (2.0f * tfy), W, H, tiles_x, tiles_y};
+        SplatRec rec; int my_radius; uint32_t tiles, dkey;
+        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, nullptr, rec, my_radius, tiles, dkey);
+        if (live) {
+            const size_t o = (size_t)v * N + idx;
+            recs[o] = rec;
+            radii[o] = my_radius;
+            tiles_touched[o] = tiles;
+            depth_keys[o] = dkey;
+            ids[o] = (uint32_t)idx;
+            if (dkey != 0xFFFFFFFFu) atomicMin(&s_min[v], dkey);
+        }
+    }
+    __syncthreads();
+    if (tid < V && s_min[tid] != 0xFFFFFFFFu) atomicMin(min_keys + 2 * tid, s_min[tid]);
 }
 
 }  // namespace
@@ -207,6 +264,27 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
     preprocess_kernel<<<blocks, PP_THREADS, smem, s>>>(va, N, M, means3D, shs, colors_precomp, opacities, scales,
                                                        rotations, cov3D_precomp, recs, radii, tiles_touched,
                                                        depth_keys, ids, min_key);
+    gs_count_launches(1);
+    GS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int gs_preprocess_multi_max_views() { return PP_MAXV; }
+
+int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int sh_degree, float scale_modifier, int N,
+                               int M, const float* means3D, const float* shs, const float* opacities,
+                               const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
+                               uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
+                               cudaStream_t s) {
+    if (N <= 0 || V <= 0) return 0;
+    if (V > PP_MAXV) { gs_set_error("preprocess_multi: V=%d > %d", V, PP_MAXV); return 1; }
+    size_t smem = (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float);
+    if (smem > 48 * 1024)
+        GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (N + PP_THREADS - 1) / PP_THREADS;
+    preprocess_multi_kernel<<<blocks, PP_THREADS, smem, s>>>(views_dev, V, W, H, sh_degree, scale_modifier, N, M, means3D,
+                                                             shs, opacities, scales, rotations, recs, radii,
+                                                             tiles_touched, depth_keys, ids, min_keys);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

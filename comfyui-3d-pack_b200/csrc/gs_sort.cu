@@ -16,9 +16,9 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 8;
 constexpr int RS_PART = RS_THREADS * RS_ITEMS;   // 4096 pairs per partition
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 4;
@@ -92,8 +92,10 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
 }
 
 // ---- one digit pass -------------------------------------------------------------
+// 512 threads x 8 items: the stable in-warp ranking is a dependent chain of (match, LDS, STS) rounds, so the
+// chain is kept short (8) and the CTA wide (16 warps) to have enough warps in flight to hide its latency.
 template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 2)
 rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
             const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
             const uint32_t* __restrict__ ghist_excl, uint32_t* __restrict__ status,
@@ -101,10 +103,10 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
             const uint32_t* __restrict__ trivial) {
     __shared__ uint32_t s_keys[RS_PART];
     __shared__ uint32_t s_vals[HAS_VALS ? RS_PART : 1];
-    __shared__ uint32_t s_whist[RS_WARPS][RS_RADIX];
+    __shared__ uint16_t s_whist[RS_WARPS][RS_RADIX];   // counts <= 256 per (warp,digit), offsets <= 4096
     __shared__ uint32_t s_start[RS_RADIX];     // block-local exclusive start of each digit
     __shared__ int64_t s_gbase[RS_RADIX];      // global position of block-sorted slot 0 of each digit, minus s_start
-    __shared__ uint32_t s_scan[RS_RADIX];
+    __shared__ uint32_t s_wtot[RS_RADIX / 32];
     __shared__ uint32_t s_part;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -119,13 +121,13 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
     }
     const uint32_t bias = key_bias ? __ldg(key_bias) : 0u;
     if (tid == 0) s_part = atomicAdd(ticket, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * RS_RADIX / 2; i += RS_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t part = s_part;
     const int64_t base = (int64_t)part * RS_PART;
     const int valid = (int)min((int64_t)RS_PART, n - base);
 
-    // warp-striped load: warp w owns [w*512, (w+1)*512) of the partition, item i lane l -> +i*32+l
+    // warp-striped load: warp w owns [w*256, (w+1)*256) of the partition, item i lane l -> +i*32+l
     uint32_t k[RS_ITEMS], v[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
     const int wbase = warp * (RS_ITEMS * 32) + lane;
@@ -145,59 +147,71 @@ rs_onesweep(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_ou
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (k[i] >> shift) & 0xFF;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        // lanes holding the same digit.  NOT match.any: MATCH is executed by a shared unit at ~128 cycles per
+        // warp instruction on sm_100 (measured: it alone accounted for the whole pass time); 8 VOTE + 8 LOP3 are free.
+        uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+            peers &= bit ? bal : ~bal;
+        }
         const uint32_t prev = s_whist[warp][d];
         __syncwarp();
         const uint32_t r = __popc(peers & lt_mask);
-        if (r == 0) s_whist[warp][d] = prev + __popc(peers);
+        if (r == 0) s_whist[warp][d] = (uint16_t)(prev + __popc(peers));
         __syncwarp();
         rank[i] = prev + r;
     }
     __syncthreads();
 
-    // thread = digit: exclusive scan over warps, block count
-    uint32_t count;
-    {
+    // threads 0..255 own one digit each: exclusive scan over warps, publish, scan over digits, look-back
+    uint32_t count = 0, pub = 0;
+    uint32_t* my_status = status + (size_t)part * RS_RADIX + tid;
+    if (tid < RS_RADIX) {
         uint32_t sum = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             const uint32_t c = s_whist[w][tid];
-            s_whist[w][tid] = sum;
+            s_whist[w][tid] = (uint16_t)sum;
             sum += c;
         }
         count = sum;
-    }
-    const uint32_t pad = (uint32_t)(RS_PART - valid);
-    const uint32_t pub = (tid == RS_RADIX - 1) ? count - pad : count;   // padding is all digit 255
-    uint32_t* my_status = status + (size_t)part * RS_RADIX + tid;
-    st_relaxed(my_status, (part == 0 ? FLAG_PFX : FLAG_AGG) | pub);
-
-    // block exclusive scan over digits (Hillis-Steele on 256 entries)
-    s_scan[tid] = count;
-    __syncthreads();
-    for (int off = 1; off < RS_RADIX; off <<= 1) {
-        const uint32_t a = (tid >= off) ? s_scan[tid - off] : 0;
-        __syncthreads();
-        s_scan[tid] += a;
-        __syncthreads();
-    }
-    const uint32_t start = s_scan[tid] - count;
-    s_start[tid] = start;
-
-    // decoupled look-back
-    uint32_t excl = 0;
-    if (part > 0) {
-        int64_t p = (int64_t)part - 1;
-        while (true) {
-            uint32_t s;
-            do { s = ld_relaxed(status + (size_t)p * RS_RADIX + tid); } while ((s & ~VAL_MASK) == 0);
-            excl += s & VAL_MASK;
-            if ((s & ~VAL_MASK) == FLAG_PFX) break;
-            p--;
+        const uint32_t pad = (uint32_t)(RS_PART - valid);
+        pub = (tid == RS_RADIX - 1) ? count - pad : count;      // padding is all digit 255
+        st_relaxed(my_status, (part == 0 ? FLAG_PFX : FLAG_AGG) | pub);
+        // exclusive scan over the 256 digits: shuffle scan per warp + 8 warp totals
+        uint32_t inc = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
         }
-        st_relaxed(my_status, FLAG_PFX | ((excl + pub) & VAL_MASK));
+        if (lane == 31) s_wtot[warp] = inc;
+        count = inc - count;                                     // warp-local exclusive
     }
-    s_gbase[tid] = (int64_t)ghist_excl[tid] + (int64_t)excl - (int64_t)start;
+    __syncthreads();
+    if (tid < RS_RADIX) {
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_RADIX / 32; w++) woff += (w < warp) ? s_wtot[w] : 0u;
+        const uint32_t start = woff + count;
+        s_start[tid] = start;
+        // decoupled look-back over earlier partitions
+        uint32_t excl = 0;
+        if (part > 0) {
+            int64_t p = (int64_t)part - 1;
+            while (true) {
+                uint32_t sflag;
+                do { sflag = ld_relaxed(status + (size_t)p * RS_RADIX + tid); } while ((sflag & ~VAL_MASK) == 0);
+                excl += sflag & VAL_MASK;
+                if ((sflag & ~VAL_MASK) == FLAG_PFX) break;
+                p--;
+            }
+            st_relaxed(my_status, FLAG_PFX | ((excl + pub) & VAL_MASK));
+        }
+        s_gbase[tid] = (int64_t)ghist_excl[tid] + (int64_t)excl - (int64_t)start;
+    }
     __syncthreads();
 
     // scatter into block-sorted order in shared memory
