@@ -27,6 +27,7 @@
 //    total in its own lane, so ONE red.global.add instruction with 10 active
 //    lanes updates the 48 B gradient record.
 #include "gs_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -180,7 +181,8 @@ __device__ __forceinline__ float xstage(float a, float b, bool hi, int m) {
     return keep + __shfl_xor_sync(0xFFFFFFFFu, send, m);
 }
 
-__global__ void __launch_bounds__(RB, 4)
+template <int MINB>
+__global__ void __launch_bounds__(RB, MINB)
 render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                        const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
@@ -316,8 +318,16 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
                               const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                               SplatGrad* sg, cudaStream_t s) {
     dim3 grid(va.tiles_x, va.tiles_y);
-    render_backward_kernel<<<grid, RB, 0, s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor,
-                                               dL_ddepth, dL_dalpha, sg);
+    static const int occ = getenv("GS_B200_BWD_OCC") ? atoi(getenv("GS_B200_BWD_OCC")) : 4;   // tuning knob: CTAs/SM target
+    if (occ >= 5)
+        render_backward_kernel<5><<<grid, RB, 0, s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor,
+                                                      dL_ddepth, dL_dalpha, sg);
+    else if (occ == 3)
+        render_backward_kernel<3><<<grid, RB, 0, s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor,
+                                                      dL_ddepth, dL_dalpha, sg);
+    else
+        render_backward_kernel<4><<<grid, RB, 0, s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor,
+                                                      dL_ddepth, dL_dalpha, sg);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
