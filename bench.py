@@ -117,7 +117,7 @@ class Clocks:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(gpu_index), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -189,10 +189,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = Clocks(local) if rank == 0 else None      # started before warm-up so it is sampling during the timed region
     for _ in range(max(args.warmup, 3)):
         pairs = step()
     barrier()
-    clocks = Clocks(local) if rank == 0 else None
     l0 = _lib.lib.gs_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
