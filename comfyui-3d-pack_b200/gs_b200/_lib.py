@@ -69,6 +69,34 @@ lib.gs_b200_profile_enable.restype = None
 lib.gs_b200_profile_enable.argtypes = [C.c_int32]
 lib.gs_b200_profile_read.restype = C.c_int32
 lib.gs_b200_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+# ---- mesh ops (include/dr_b200.h) -------------------------------------------------------------------------
+_I = C.c_int32
+lib.dr_b200_rasterize_scratch_bytes.restype = C.c_size_t
+lib.dr_b200_rasterize_scratch_bytes.argtypes = [_I, _I, _I, _I]
+lib.dr_b200_rasterize_fwd.restype = _I
+lib.dr_b200_rasterize_fwd.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]
+lib.dr_b200_rasterize_bwd.restype = _I
+lib.dr_b200_rasterize_bwd.argtypes = [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]
+lib.dr_b200_interpolate_fwd.restype = _I
+lib.dr_b200_interpolate_fwd.argtypes = [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]
+lib.dr_b200_interpolate_bwd.restype = _I
+lib.dr_b200_interpolate_bwd.argtypes = [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]
+lib.dr_b200_texture_fwd.restype = _I
+lib.dr_b200_texture_fwd.argtypes = [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P]
+lib.dr_b200_texture_bwd.restype = _I
+lib.dr_b200_texture_bwd.argtypes = [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P]
+lib.dr_b200_topology_scratch_bytes.restype = C.c_size_t
+lib.dr_b200_topology_scratch_bytes.argtypes = [_I]
+lib.dr_b200_edge_opposites.restype = _I
+lib.dr_b200_edge_opposites.argtypes = [_P, _I, _I, _P, _P, _P]
+lib.dr_b200_antialias_fwd.restype = _I
+lib.dr_b200_antialias_fwd.argtypes = [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]
+lib.dr_b200_antialias_bwd.restype = _I
+lib.dr_b200_antialias_bwd.argtypes = [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]
+DR_EXPORTS = ["dr_b200_rasterize_scratch_bytes", "dr_b200_rasterize_fwd", "dr_b200_rasterize_bwd",
+              "dr_b200_interpolate_fwd", "dr_b200_interpolate_bwd", "dr_b200_texture_fwd", "dr_b200_texture_bwd",
+              "dr_b200_topology_scratch_bytes", "dr_b200_edge_opposites", "dr_b200_antialias_fwd", "dr_b200_antialias_bwd"]
+
 NSTAGES = 9
 STAGE_NAMES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "composite_fwd",
                "composite_bwd", "preprocess_bwd"]
