@@ -97,6 +97,35 @@ DR_EXPORTS = ["dr_b200_rasterize_scratch_bytes", "dr_b200_rasterize_fwd", "dr_b2
               "dr_b200_interpolate_fwd", "dr_b200_interpolate_bwd", "dr_b200_texture_fwd", "dr_b200_texture_bwd",
               "dr_b200_topology_scratch_bytes", "dr_b200_edge_opposites", "dr_b200_antialias_fwd", "dr_b200_antialias_bwd"]
 
+# ---- Instant-NGP path (include/ngp_b200.h) -----------------------------------------------------------------
+_L = C.c_int64
+_F = C.c_float
+lib.ngp_b200_grid_encode_fwd.restype = _I
+lib.ngp_b200_grid_encode_fwd.argtypes = [_P, _L, _P, _P, _I, _F, _F, _I, _P, _P]
+lib.ngp_b200_grid_encode_bwd.restype = _I
+lib.ngp_b200_grid_encode_bwd.argtypes = [_P, _L, _P, _I, _F, _F, _I, _P, _P, _P]
+lib.ngp_b200_grid_tv_grad.restype = _I
+lib.ngp_b200_grid_tv_grad.argtypes = [_P, _L, _P, _P, _I, _F, _F, _I, _F, _P, _P]
+lib.ngp_b200_march_scratch_bytes.restype = C.c_size_t
+lib.ngp_b200_march_scratch_bytes.argtypes = [_L, _I]
+lib.ngp_b200_march_count.restype = _I
+lib.ngp_b200_march_count.argtypes = [_P, _P, _L, _P, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P]
+lib.ngp_b200_march_write.restype = _I
+lib.ngp_b200_march_write.argtypes = [_P, _P, _L, _I, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]
+lib.ngp_b200_ray_ranges.restype = _I
+lib.ngp_b200_ray_ranges.argtypes = [_P, _L, _L, _P, _P]
+lib.ngp_b200_weights_fwd.restype = _I
+lib.ngp_b200_weights_fwd.argtypes = [_P, _P, _P, _P, _L, _P, _P, _P, _P]
+lib.ngp_b200_weights_bwd.restype = _I
+lib.ngp_b200_weights_bwd.argtypes = [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P]
+lib.ngp_b200_accumulate_fwd.restype = _I
+lib.ngp_b200_accumulate_fwd.argtypes = [_P, _P, _I, _P, _L, _P, _P]
+lib.ngp_b200_accumulate_bwd.restype = _I
+lib.ngp_b200_accumulate_bwd.argtypes = [_P, _P, _I, _P, _L, _P, _P, _P, _P]
+NGP_EXPORTS = ["ngp_b200_grid_encode_fwd", "ngp_b200_grid_encode_bwd", "ngp_b200_grid_tv_grad", "ngp_b200_march_scratch_bytes",
+               "ngp_b200_march_count", "ngp_b200_march_write", "ngp_b200_ray_ranges", "ngp_b200_weights_fwd",
+               "ngp_b200_weights_bwd", "ngp_b200_accumulate_fwd", "ngp_b200_accumulate_bwd"]
+
 NSTAGES = 9
 STAGE_NAMES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "composite_fwd",
                "composite_bwd", "preprocess_bwd"]

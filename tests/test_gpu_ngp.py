@@ -1,0 +1,171 @@
+"""GPU parity tests of the Instant-NGP path against oracle/ngp_oracle.py, through the C ABI (include/ngp_b200.h)
+via the kiui / nerfacc shims.  Packed sample lists bit-exact; features, weights, gradients within tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT  # noqa: F401
+from oracle import gs_oracle as O
+from oracle import ngp_oracle as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return float((a.detach().cpu().double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("L", [4, 12, 16])
+def test_grid_encode_forward_backward_and_tv(dev, L):
+    from kiui.gridencoder import GridEncoder
+    torch.manual_seed(L)
+    enc = GridEncoder(num_levels=L).to(dev)
+    enc.embeddings.data.uniform_(-1, 1)
+    off = G.grid_offsets(num_levels=L)
+    assert np.array_equal(off, enc._offsets_np.astype(np.int64))
+    x = torch.rand(5000, 3) * 2 - 1
+    x[:4] = torch.tensor([[-1.0, -1, -1], [1, 1, 1], [0, 0, 0], [1, -1, 0.5]])        # box corners / faces
+    emb = enc.embeddings.detach().cpu()
+    ref = G.grid_encode(x, emb, off, num_levels=L)
+    out = enc(x.to(dev))
+    assert out.shape == (5000, 2 * L)
+    assert float((out.detach().cpu() - ref).abs().max()) < 2e-5
+    gout = torch.rand(5000, 2 * L)
+    e = emb.clone().requires_grad_(True)
+    (G.grid_encode(x, e, off, num_levels=L) * gout).sum().backward()
+    (out * gout.to(dev)).sum().backward()
+    assert _rel(enc.embeddings.grad, e.grad) < 1e-5
+    # prefix shapes and bound
+    o2 = enc(x.to(dev).view(50, 100, 3) * 0.5, bound=0.5)
+    assert o2.shape == (50, 100, 2 * L) and float((o2.reshape(-1, 2 * L) - out).abs().max()) < 1e-6
+    # total-variation gradient, explicit sample points
+    xs = torch.rand(3000, 3) * 2 - 1
+    g0 = enc.embeddings.grad.clone()
+    enc.grad_total_variation(1e-3, inputs=xs.to(dev))
+    ref_tv = G.grad_total_variation(xs, emb, off, 1e-3, num_levels=L)
+    assert float(((enc.embeddings.grad - g0).cpu() - ref_tv).abs().max()) < 1e-6
+    enc.grad_total_variation(1e-8)                              # the reference's call form (Instant_NGP.py:195)
+
+
+def _binary_ball(R, radius):
+    g = (torch.arange(R).float() + 0.5) / R * 2 - 1
+    x, y, z = torch.meshgrid(g, g, g, indexing="ij")
+    return (x * x + y * y + z * z) < radius * radius
+
+
+@pytest.mark.parametrize("R,h,w,strat", [(64, 24, 32, False), (32, 40, 40, True)])
+def test_marching_sample_list_bit_exact(dev, R, h, w, strat):
+    from gs_b200 import ngp
+    binary = _binary_ball(R, 0.6)
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    ro, rd = G.get_rays(O.orbit_camera(15, 40, 1.75), h, w, 49.1)
+    toff = torch.rand(h * w, generator=torch.Generator().manual_seed(1)) * 5e-3 if strat else None
+    ri_r, ts_r, te_r = G.march(ro, rd, binary, aabb, 0.01, 100.0, 5e-3, toff)
+    ri, ts, te = ngp.march_rays(ro.to(dev), rd.to(dev), binary.to(dev), aabb.to(dev), 0.01, 100.0, 5e-3,
+                                None if toff is None else toff.to(dev))
+    assert ri.dtype == torch.int64 and ri.numel() == ri_r.numel() > 1000
+    assert torch.equal(ri.cpu(), ri_r)
+    assert torch.equal(ts.cpu(), ts_r) and torch.equal(te.cpu(), te_r)           # bit-exact floats by construction
+    assert bool((ri[1:] >= ri[:-1]).all())
+
+
+def test_weights_accumulate_forward_backward(dev):
+    import nerfacc
+    g = torch.Generator().manual_seed(0)
+    n_rays = 500
+    cnt = torch.randint(0, 40, (n_rays,), generator=g)
+    ri = torch.repeat_interleave(torch.arange(n_rays), cnt)
+    S = ri.numel()
+    ts = torch.rand(S, generator=g) * 3; te = ts + 0.005 + torch.rand(S, generator=g) * 0.01
+    sig = torch.rand(S, generator=g) * 50
+    vals = torch.rand(S, 3, generator=g)
+    gc = torch.rand(n_rays, 3, generator=g); ga = torch.rand(n_rays, 1, generator=g); gt = torch.rand(S, generator=g) * 0.1
+    sr = sig.clone().requires_grad_(True); vr = vals.clone().requires_grad_(True)
+    w, T, a = G.render_weight_from_density(ts, te, sr, ri, n_rays)
+    col = G.accumulate_along_rays(w, vr, ri, n_rays); alp = G.accumulate_along_rays(w, None, ri, n_rays)
+    ((col * gc).sum() + (alp * ga).sum() + (T * gt).sum()).backward()
+    sg = sig.to(dev).requires_grad_(True); vg = vals.to(dev).requires_grad_(True)
+    w2, T2, a2 = nerfacc.render_weight_from_density(ts.to(dev), te.to(dev), sg, ray_indices=ri.to(dev), n_rays=n_rays)
+    col2 = nerfacc.accumulate_along_rays(w2, values=vg, ray_indices=ri.to(dev), n_rays=n_rays)
+    alp2 = nerfacc.accumulate_along_rays(w2, values=None, ray_indices=ri.to(dev), n_rays=n_rays)
+    ((col2 * gc.to(dev)).sum() + (alp2 * ga.to(dev)).sum() + (T2 * gt.to(dev)).sum()).backward()
+    assert float((w2.detach().cpu() - w.detach()).abs().max()) < 1e-6 and float((T2.detach().cpu() - T.detach()).abs().max()) < 1e-6
+    assert float((col2.detach().cpu() - col.detach()).abs().max()) < 1e-5 and float((alp2.detach().cpu() - alp.detach()).abs().max()) < 1e-5
+    assert _rel(sg.grad, sr.grad) < 1e-4 and _rel(vg.grad, vr.grad) < 1e-5
+
+
+def test_render_nerf_call_sequence_matches_oracle(dev):
+    """InstantNGP.render_nerf (Instant_NGP.py:101-156) with the shims vs the same sequence on the oracle."""
+    import nerfacc
+    from kiui.gridencoder import GridEncoder
+    from kiui.nn import MLP, trunc_exp
+    torch.manual_seed(0)
+    h = w = 32
+    enc_d, enc_c = GridEncoder(num_levels=12).to(dev), GridEncoder(num_levels=12).to(dev)
+    enc_d.embeddings.data.uniform_(-0.5, 0.5); enc_c.embeddings.data.uniform_(-0.5, 0.5)
+    mlp_d, mlp_c = MLP(24, 1, 32, 2, bias=False).to(dev), MLP(24, 3, 32, 2, bias=False).to(dev)
+    est = nerfacc.OccGridEstimator(roi_aabb=torch.tensor([-1.0, -1, -1, 1, 1, 1], device=dev), resolution=64, levels=1).to(dev)
+    est.binaries = _binary_ball(64, 0.6).to(dev)[None]
+    est.occs = est.binaries.flatten().float()
+    ro, rd = G.get_rays(O.orbit_camera(0, 30, 1.75), h, w, 49.1)
+    rog, rdg = ro.to(dev), rd.to(dev)
+
+    def density(xs):
+        return trunc_exp(mlp_d(enc_d(xs))).squeeze(-1)
+
+    def sigma_fn(t0, t1, ri):
+        return density(rog[ri] + rdg[ri] * (t0 + t1)[:, None] / 2.0)
+    with torch.no_grad():
+        ri, t0, t1 = est.sampling(rog, rdg, sigma_fn=sigma_fn, near_plane=0.01, far_plane=100, render_step_size=5e-3,
+                                  stratified=False, cone_angle=0)
+    xs = rog[ri] + rdg[ri] * (t0 + t1)[:, None] / 2.0
+    sig = density(xs); rgb = torch.sigmoid(mlp_c(enc_c(xs)))
+    wts, T, al = nerfacc.render_weight_from_density(t0, t1, sig, ray_indices=ri, n_rays=h * w)
+    color = nerfacc.accumulate_along_rays(wts, values=rgb, ray_indices=ri, n_rays=h * w)
+    alpha = nerfacc.accumulate_along_rays(wts, values=None, ray_indices=ri, n_rays=h * w)
+    color = color + (1.0 - alpha) * 1.0
+    gimg = torch.rand(h * w, 3, generator=torch.Generator().manual_seed(5))
+    ((color * gimg.to(dev)).sum() + 0.1 * (alpha ** 2).sum()).backward()
+
+    # oracle replay with the same parameters and the same sample list
+    off = G.grid_offsets(num_levels=12)
+    ed = enc_d.embeddings.detach().cpu().clone().requires_grad_(True); ec = enc_c.embeddings.detach().cpu().clone().requires_grad_(True)
+    Wd = [l.weight.detach().cpu() for l in mlp_d.net]; Wc = [l.weight.detach().cpu() for l in mlp_c.net]
+    def mlp(W, x):
+        return torch.relu(x @ W[0].T) @ W[1].T
+    ri_r, t0_r, t1_r = G.march(ro, rd, _binary_ball(64, 0.6), torch.tensor([-1.0, -1, -1, 1, 1, 1]), 0.01, 100.0, 5e-3)
+    xs_r = ro[ri_r] + rd[ri_r] * (t0_r + t1_r)[:, None] / 2.0
+    with torch.no_grad():
+        s0 = G.trunc_exp(mlp(Wd, G.grid_encode(xs_r, ed.detach(), off, num_levels=12))).squeeze(-1)
+        m = G.visibility_mask(t0_r, t1_r, s0, ri_r, h * w, 1e-4, 0.0)
+    ri_r, t0_r, t1_r = ri_r[m], t0_r[m], t1_r[m]
+    assert ri.numel() == ri_r.numel() and torch.equal(ri.cpu(), ri_r) and torch.equal(t0.cpu(), t0_r)
+    xs_r = ro[ri_r] + rd[ri_r] * (t0_r + t1_r)[:, None] / 2.0
+    sig_r = G.trunc_exp(mlp(Wd, G.grid_encode(xs_r, ed, off, num_levels=12))).squeeze(-1)
+    rgb_r = torch.sigmoid(mlp(Wc, G.grid_encode(xs_r, ec, off, num_levels=12)))
+    w_r, _, _ = G.render_weight_from_density(t0_r, t1_r, sig_r, ri_r, h * w)
+    col_r = G.accumulate_along_rays(w_r, rgb_r, ri_r, h * w); alp_r = G.accumulate_along_rays(w_r, None, ri_r, h * w)
+    col_r = col_r + (1.0 - alp_r)
+    ((col_r * gimg).sum() + 0.1 * (alp_r ** 2).sum()).backward()
+    assert float((color.detach().cpu() - col_r.detach()).abs().max()) < 1e-4
+    assert float((alpha.detach().cpu() - alp_r.detach()).abs().max()) < 1e-4
+    assert _rel(enc_d.embeddings.grad, ed.grad) < 1e-3 and _rel(enc_c.embeddings.grad, ec.grad) < 1e-3
+
+
+def test_occupancy_grid_update_host_logic(dev):
+    import nerfacc
+    est = nerfacc.OccGridEstimator(roi_aabb=torch.tensor([-1.0, -1, -1, 1, 1, 1], device=dev), resolution=16, levels=1).to(dev)
+    est.train()
+    ball = lambda x: (x.norm(dim=-1, keepdim=True) < 0.5).float() * 0.05
+    est.update_every_n_steps(0, occ_eval_fn=ball, occ_thre=0.01, n=8)
+    inside = _binary_ball(16, 0.35).to(dev); outside = ~_binary_ball(16, 0.7).to(dev)
+    assert bool(est.binaries[0][inside].all()) and not bool(est.binaries[0][outside].any())
+    est.update_every_n_steps(3, occ_eval_fn=ball, occ_thre=0.01, n=8)        # not a multiple of n: no-op
+    est.update_every_n_steps(512, occ_eval_fn=ball, occ_thre=0.01, n=8)      # post-warm-up branch
+    assert bool(est.binaries[0][inside].all())
