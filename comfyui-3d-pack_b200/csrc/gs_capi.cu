@@ -665,4 +665,23 @@ int32_t gs_b200_step_host_dev_grads(int32_t V, int32_t H, int32_t W, int32_t sh_
                           images_host, num_rendered_out, stream_);
 }
 
+// ---- optimisation-step kernels (gs_train.cu) -------------------------------------------------------------
+
+int32_t gs_b200_activate(int32_t N, const float* raw_opacities, const float* raw_scales, const float* raw_rotations,
+                         float* opacities, float* scales, float* rotations, void* stream_) {
+    if (N > 0 && (!raw_opacities || !raw_scales || !raw_rotations || !opacities || !scales || !rotations)) { gs_set_error("activate: NULL"); return 1; }
+    return gs_launch_activate(N, raw_opacities, raw_scales, raw_rotations, opacities, scales, rotations, (cudaStream_t)stream_);
+}
+int32_t gs_b200_adam_step(int32_t N, int32_t M, const float* lrs6_host, float beta1, float beta2, float eps, int32_t step,
+                          float grad_scale, const float* grads_packed, float* params_packed, float* exp_avg,
+                          float* exp_avg_sq, void* stream_) {
+    if (!lrs6_host || step < 1 || (N > 0 && (!grads_packed || !params_packed || !exp_avg || !exp_avg_sq))) { gs_set_error("adam_step: bad argument"); return 1; }
+    return gs_launch_adam(N, M, lrs6_host, beta1, beta2, eps, step, grad_scale, grads_packed, params_packed, exp_avg, exp_avg_sq, (cudaStream_t)stream_);
+}
+int32_t gs_b200_densify_stats(int32_t N, const float* dL_dmeans2D, const int32_t* radii, float* xyz_gradient_accum,
+                              float* denom, float* max_radii2D, void* stream_) {
+    if (N > 0 && (!dL_dmeans2D || !radii || !xyz_gradient_accum || !denom || !max_radii2D)) { gs_set_error("densify_stats: NULL"); return 1; }
+    return gs_launch_densify_stats(N, dL_dmeans2D, radii, xyz_gradient_accum, denom, max_radii2D, (cudaStream_t)stream_);
+}
+
 }  // extern "C"

@@ -159,6 +159,10 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
                                         const SplatGrad* sg, float* dmeans3D, float* dmeans2D, float* dshs,
                                         float* dopac, float* dscales, float* drots, int accumulate, cudaStream_t s);
 
+int gs_launch_activate(int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+int gs_launch_adam(int, int, const float*, float, float, float, int, float, const float*, float*, float*, float*, cudaStream_t);
+int gs_launch_densify_stats(int, const float*, const int32_t*, float*, float*, float*, cudaStream_t);
+
 size_t gs_sort_scratch_bytes(int64_t n);
 int gs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t n,
                       int begin_bit, int end_bit, void* scratch, int* result_in_alt, cudaStream_t s);

@@ -126,6 +126,14 @@ NGP_EXPORTS = ["ngp_b200_grid_encode_fwd", "ngp_b200_grid_encode_bwd", "ngp_b200
                "ngp_b200_march_count", "ngp_b200_march_write", "ngp_b200_ray_ranges", "ngp_b200_weights_fwd",
                "ngp_b200_weights_bwd", "ngp_b200_accumulate_fwd", "ngp_b200_accumulate_bwd"]
 
+lib.gs_b200_activate.restype = _I
+lib.gs_b200_activate.argtypes = [_I, _P, _P, _P, _P, _P, _P, _P]
+lib.gs_b200_adam_step.restype = _I
+lib.gs_b200_adam_step.argtypes = [_I, _I, _P, _F, _F, _F, _I, _F, _P, _P, _P, _P, _P]
+lib.gs_b200_densify_stats.restype = _I
+lib.gs_b200_densify_stats.argtypes = [_I, _P, _P, _P, _P, _P, _P]
+TRAIN_EXPORTS = ["gs_b200_activate", "gs_b200_adam_step", "gs_b200_densify_stats"]
+
 NSTAGES = 9
 STAGE_NAMES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "composite_fwd",
                "composite_bwd", "preprocess_bwd"]

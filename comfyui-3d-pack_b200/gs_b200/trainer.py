@@ -1,0 +1,205 @@
+"""B200-native optimisation loop around the rasterizer: the fast path for what GaussianModel +
+GaussianSplatting3D.training do in the reference (MVs_Algorithms/GaussianSplatting/main_3DGS_renderer.py:236-781,
+main_3DGS.py:86-232).  The reference's own Python runs unmodified over the `diff_gaussian_rasterization` shim; this
+module is the packed-layout alternative: one raw-parameter buffer, fused activation, multi-view pipelined
+forward/backward (gs_b200_step_device), fused chain-rule + Adam (gs_b200_adam_step), fused densification
+statistics, torch-side clone/split/prune (every 100 steps).  Losses are torch ops (gs_b200.losses).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, camera, losses, optim_step
+from .rasterizer import _ptr, _stream, knn_mean_dist2
+
+SH_C0 = 0.28209479177387814
+
+
+def expon_lr(step, lr_init, lr_final, delay_mult=1.0, max_steps=30000, delay_steps=0):
+    """get_expon_lr_func (main_3DGS_renderer.py:21-43)."""
+    if lr_init == lr_final:
+        return lr_init
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    delay = delay_mult + (1 - delay_mult) * np.sin(0.5 * np.pi * np.clip(step / delay_steps, 0, 1)) if delay_steps > 0 else 1.0
+    t = np.clip(step / max_steps, 0, 1)
+    return float(delay * np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t))
+
+
+class TrainParams:
+    """GSParams defaults (main_3DGS.py:15-74)."""
+
+    def __init__(self, **kw):
+        d = dict(training_iterations=30000, batch_size=1, lambda_ssim=0.2, lambda_alpha=3.0, feature_lr=0.0025, opacity_lr=0.05,
+                 scaling_lr=0.005, rotation_lr=0.001, position_lr_init=0.00016, position_lr_final=0.0000016,
+                 position_lr_delay_mult=0.01, position_lr_max_steps=30000, num_pts=10000, percent_dense=0.01,
+                 density_start_iter=500, density_end_iter=15000, densification_interval=100, opacity_reset_interval=3000,
+                 densify_grad_threshold=0.0002, sh_degree=3, spatial_lr_scale=10.0)
+        d.update(kw)
+        self.__dict__.update(d)
+
+
+class GaussianTrainer:
+    GROUPS = ("xyz", "shs", "opacity", "scaling", "rotation")
+
+    def __init__(self, params: TrainParams = None, device="cuda", seed=0):
+        self.p = params or TrainParams()
+        self.device = torch.device(device)
+        self.M = (self.p.sh_degree + 1) ** 2
+        self.step_count = 0
+        self._init_random(self.p.num_pts, seed)
+
+    # ---------------------------------------------------------------- packed storage
+    def _sizes(self, n):
+        return [3 * n, 3 * self.M * n, n, 3 * n, 4 * n]
+
+    def _views(self, buf, n):
+        out, o = {}, 0
+        for name, s, shp in zip(self.GROUPS, self._sizes(n), [(n, 3), (n, self.M, 3), (n, 1), (n, 3), (n, 4)]):
+            out[name] = buf[o:o + s].view(*shp); o += s
+        return out
+
+    def _alloc(self, n):
+        tot = sum(self._sizes(n))
+        self.N = n
+        self.raw = torch.zeros(tot, device=self.device)
+        self.m1 = torch.zeros(tot, device=self.device); self.m2 = torch.zeros(tot, device=self.device)
+        self.v = self._views(self.raw, n)
+        self.act = torch.zeros(8 * n, device=self.device)                       # activated opac | scales | rots
+        self.a_opac, self.a_scales, self.a_rots = self.act[:n].view(n, 1), self.act[n:4 * n].view(n, 3), self.act[4 * n:].view(n, 4)
+        self.grads = torch.zeros(tot + 3 * n, device=self.device)               # + means2D
+        self.g_means2D = self.grads[tot:].view(n, 3)
+        self.radii = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self.grad_accum = torch.zeros(n, device=self.device); self.denom = torch.zeros(n, device=self.device)
+        self.max_radii2D = torch.zeros(n, device=self.device)
+
+    def _init_random(self, n, seed):
+        """initialize(None, num_pts) + create_from_pcd (main_3DGS_renderer.py:811-826, 407-433)."""
+        rng = np.random.RandomState(seed)
+        phis = rng.random_sample((n,)) * 2 * np.pi
+        thetas = np.arccos(rng.random_sample((n,)) * 2 - 1)
+        r = 0.5 * np.cbrt(rng.random_sample((n,)))
+        xyz = np.stack((r * np.sin(thetas) * np.cos(phis), r * np.sin(thetas) * np.sin(phis), r * np.cos(thetas)), 1).astype(np.float32)
+        col = (rng.random_sample((n, 3)) / 255.0) * SH_C0 + 0.5
+        self._alloc(n)
+        self.v["xyz"].copy_(torch.from_numpy(xyz))
+        self.v["shs"][:, 0, :] = torch.from_numpy(((col - 0.5) / SH_C0).astype(np.float32)).to(self.device)
+        d2 = torch.clamp_min(knn_mean_dist2(self.v["xyz"]), 1e-7)
+        self.v["scaling"].copy_(torch.log(torch.sqrt(d2))[:, None].repeat(1, 3))
+        self.v["rotation"][:, 0] = 1.0
+        self.v["opacity"].fill_(math.log(0.1 / 0.9))
+
+    # ---------------------------------------------------------------- one optimisation step
+    def activate(self):
+        _lib.check(_lib.lib.gs_b200_activate(self.N, _ptr(self.v["opacity"]), _ptr(self.v["scaling"]), _ptr(self.v["rotation"]),
+                                             _ptr(self.a_opac), _ptr(self.a_scales), _ptr(self.a_rots), _stream()))
+
+    def learning_rates(self, step):
+        p = self.p
+        lr_xyz = expon_lr(step, p.position_lr_init * p.spatial_lr_scale, p.position_lr_final * p.spatial_lr_scale,
+                          p.position_lr_delay_mult, p.position_lr_max_steps)
+        return np.array([lr_xyz, p.feature_lr, p.feature_lr / 20.0, p.opacity_lr, p.scaling_lr, p.rotation_lr], dtype=np.float32)
+
+    def render_views(self, views_np, W, H, need_grad_fn=None):
+        """Forward all views (images kept), call need_grad_fn(images[V,5,H,W]) -> dL/dimages, then backward.
+        Returns images (detached)."""
+        V = views_np.shape[0]
+        views = optim_step.ViewSet(np.ascontiguousarray(views_np, dtype=np.float32), W, H, self.p.sh_degree, self.device)
+        cloud = optim_step.PackedParams.__new__(optim_step.PackedParams)
+        cloud.means3D, cloud.shs, cloud.opacities, cloud.scales, cloud.rotations = self.v["xyz"], self.v["shs"], self.a_opac, self.a_scales, self.a_rots
+        cloud.N, cloud.M, cloud.grads, cloud.radii = self.N, self.M, self.grads, self.radii
+        imgs = torch.empty(V, 5, H, W, device=self.device)
+        # pass 1: forward only (zero upstream gradient), to evaluate the loss
+        self.activate()
+        zero = torch.zeros(V, 5, H, W, device=self.device)
+        optim_step.step_device_pipelined(cloud, views, zero, imgs)
+        if need_grad_fn is None:
+            return imgs
+        dl = need_grad_fn(imgs)
+        optim_step.step_device_pipelined(cloud, views, dl.contiguous(), imgs)
+        return imgs
+
+    def train_step(self, views_np, W, H, ref_images, ref_masks, world=1):
+        """ref_images [V,3,H,W], ref_masks [V,1,H,W] on device.  Returns the loss value (python float)."""
+        p = self.p
+        box = {}
+
+        def grad_fn(imgs):
+            x = imgs.detach().clone().requires_grad_(True)
+            loss = losses.training_loss(x[:, :3].clamp(0, 1), x[:, 4:5], ref_images, ref_masks, p.lambda_ssim, p.lambda_alpha)
+            loss.backward()
+            box["loss"] = float(loss.detach())
+            return x.grad
+        self.render_views(views_np, W, H, grad_fn)
+        self.step_count += 1
+        lrs = self.learning_rates(self.step_count - 1)
+        _lib.check(_lib.lib.gs_b200_adam_step(self.N, self.M, C.c_void_p(lrs.ctypes.data), 0.9, 0.999, 1e-15, self.step_count, 1.0 / world,
+                                              _ptr(self.grads), _ptr(self.raw), _ptr(self.m1), _ptr(self.m2), _stream()))
+        s = self.step_count - 1
+        if p.density_start_iter <= s <= p.density_end_iter:
+            # NOTE: radii of the LAST view of the batch, as the reference (main_3DGS.py:211) — here also the summed means2D grad
+            _lib.check(_lib.lib.gs_b200_densify_stats(self.N, _ptr(self.g_means2D), _ptr(self.radii), _ptr(self.grad_accum),
+                                                      _ptr(self.denom), _ptr(self.max_radii2D), _stream()))
+            if s % p.densification_interval == 0:
+                self.densify_and_prune(p.densify_grad_threshold, 0.005, 4.0, 1.0)
+            if s % p.opacity_reset_interval == 0:
+                self.reset_opacity()
+        return box["loss"]
+
+    # ---------------------------------------------------------------- densification (torch-side, infrequent)
+    def _rebuild(self, keep_idx, new):
+        """keep rows `keep_idx` of every group (+Adam moments), append `new` rows (zero moments)."""
+        old_v, old_m1, old_m2, n_old = self.v, self._views(self.m1, self.N), self._views(self.m2, self.N), self.N
+        n_new = keep_idx.numel() + (new["xyz"].shape[0] if new else 0)
+        raws = {k: old_v[k][keep_idx] for k in self.GROUPS}
+        m1s = {k: old_m1[k][keep_idx] for k in self.GROUPS}; m2s = {k: old_m2[k][keep_idx] for k in self.GROUPS}
+        self._alloc(n_new)
+        nm1, nm2 = self._views(self.m1, n_new), self._views(self.m2, n_new)
+        k0 = keep_idx.numel()
+        for k in self.GROUPS:
+            self.v[k][:k0] = raws[k]; nm1[k][:k0] = m1s[k]; nm2[k][:k0] = m2s[k]
+            if new:
+                self.v[k][k0:] = new[k]
+
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, generator=None):
+        """densify_by_clone_and_split + prune (main_3DGS_renderer.py:641-668, 752-781)."""
+        p = self.p
+        grads = self.grad_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        scal = torch.exp(self.v["scaling"]).max(dim=1).values
+        big = scal > p.percent_dense * extent
+        clone = (grads >= max_grad) & ~big
+        split = (grads >= max_grad) & big                       # evaluated on the pre-clone set: clones carry zero grad
+        idx_c = torch.nonzero(clone)[:, 0]; idx_s = torch.nonzero(split)[:, 0]
+        new = {k: self.v[k][idx_c].clone() for k in self.GROUPS}
+        if idx_s.numel():
+            Nn = 2
+            stds = torch.exp(self.v["scaling"][idx_s]).repeat(Nn, 1)
+            samples = torch.normal(torch.zeros_like(stds), stds, generator=generator)
+            q = self.v["rotation"][idx_s]
+            q = q / q.norm(dim=1, keepdim=True)
+            r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), 2 * (x * y + r * z), 1 - 2 * (x * x + z * z),
+                             2 * (y * z - r * x), 2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3).repeat(Nn, 1, 1)
+            sp = {"xyz": torch.bmm(R, samples.unsqueeze(-1)).squeeze(-1) + self.v["xyz"][idx_s].repeat(Nn, 1),
+                  "scaling": torch.log(torch.exp(self.v["scaling"][idx_s]).repeat(Nn, 1) / (0.8 * Nn)),
+                  "rotation": self.v["rotation"][idx_s].repeat(Nn, 1), "shs": self.v["shs"][idx_s].repeat(Nn, 1, 1),
+                  "opacity": self.v["opacity"][idx_s].repeat(Nn, 1)}
+            new = {k: torch.cat([new[k], sp[k]], dim=0) for k in self.GROUPS}
+        # prune: split parents, low opacity, big on screen / in world (new points have max_radii2D = 0)
+        n_old = self.N
+        opac = torch.sigmoid(self.v["opacity"]).squeeze(1)
+        prune_old = split | (opac < min_opacity) | (self.max_radii2D > max_screen_size) | (scal > 0.1 * extent)
+        n_op = torch.sigmoid(new["opacity"]).squeeze(1); n_sc = torch.exp(new["scaling"]).max(dim=1).values
+        keep_new = ~((n_op < min_opacity) | (n_sc > 0.1 * extent))
+        new = {k: v[keep_new] for k, v in new.items()}
+        self._rebuild(torch.nonzero(~prune_old)[:, 0], new)
+        return dict(cloned=int(idx_c.numel()), split=int(idx_s.numel()), pruned=int(prune_old.sum()), n=self.N, n_before=n_old)
+
+    def reset_opacity(self):
+        o = torch.sigmoid(self.v["opacity"])
+        o = torch.minimum(o, torch.full_like(o, 0.01))
+        self.v["opacity"].copy_(torch.log(o / (1 - o)))
+        self._views(self.m1, self.N)["opacity"].zero_(); self._views(self.m2, self.N)["opacity"].zero_()
