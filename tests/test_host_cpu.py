@@ -115,3 +115,26 @@ def test_host_camera_matches_reference_fixtures_and_oracle():
     assert np.allclose(v[1, :16], st.viewmatrix.reshape(-1).numpy(), atol=1e-6)
     assert np.allclose(v[1, 16:32], st.projmatrix.reshape(-1).numpy(), atol=1e-5)
     assert abs(v[1, 38] - st.tanfovx) < 1e-6 and abs(v[1, 39] - st.tanfovy) < 1e-6
+
+
+def test_gs_ply_wire_format_roundtrip_and_property_order(tmp_path):
+    from gs_b200 import ply
+    g = torch.Generator().manual_seed(0)
+    N, M = 37, 16
+    d = dict(xyz=torch.randn(N, 3, generator=g), shs=torch.randn(N, M, 3, generator=g), opacity=torch.randn(N, 1, generator=g),
+             scaling=torch.randn(N, 3, generator=g), rotation=torch.randn(N, 4, generator=g))
+    path = str(tmp_path / "g.ply")
+    ply.write_gs_ply(path, **d)
+    head = open(path, "rb").read(4096).split(b"end_header\n")[0].decode().splitlines()
+    props = [l.split()[-1] for l in head if l.startswith("property")]
+    # mesh_utils.py:333-344 (construct_list_of_gs_attributes) order
+    assert props[:9] == ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"]
+    assert props[9] == "f_rest_0" and props[9 + 44] == "f_rest_44" and props[-8:] == ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    assert all(l.startswith("property float ") for l in head if l.startswith("property"))
+    back = ply.read_gs_ply(path)
+    for k in d:
+        assert torch.equal(back[k], d[k]), k
+    # channel-major SH planes, as to_ply's transpose(1,2).flatten (main_3DGS_renderer.py:475-484)
+    rows = ply.pack_rows(**d)
+    assert float(rows[5, 9 + 1 * 15 + 3]) == float(d["shs"][5, 4, 1])          # f_rest_{c*(M-1)+k} = coeff k+1 of channel c
+    assert ply.max_sh_degree_from_properties(45) == 3 and ply.max_sh_degree_from_properties(0) == 0
