@@ -294,24 +294,25 @@ preprocess_backward_multi_kernel(const float* __restrict__ views, int V, int W, 
                                  const float* __restrict__ rotations, const int32_t* __restrict__ radii,
                                  const SplatGrad* __restrict__ sg, float* __restrict__ dmeans3D,
                                  float* __restrict__ dmeans2D, float* __restrict__ dshs, float* __restrict__ dopac,
-                                 float* __restrict__ dscales, float* __restrict__ drots, int accumulate) {
+                                 float* __restrict__ dscales, float* __restrict__ drots, int accumulate, int first,
+                                 int count) {
     extern __shared__ __align__(16) float s_all[];    // [128][rowp] SH in, then [128][rowp] dSH accumulators
     __shared__ float s_views[PB_MAXV * 40];
     const int tid = threadIdx.x;
-    const int base = blockIdx.x * PB_THREADS;
+    const int base = first + blockIdx.x * PB_THREADS;       // Gaussian range [first, first+count), first % 128 == 0
     const int row = 3 * M;
     const int rowp = gs_rowp(row);
     float* s_sh = s_all;
     float* s_dsh = s_all + PB_THREADS * rowp;
     for (int i = tid; i < V * 40; i += PB_THREADS) s_views[i] = __ldg(views + i);
-    const int cnt = min(PB_THREADS, N - base);
+    const int cnt = min(PB_THREADS, first + count - base);
     const size_t goff = (size_t)base * row;
     gs_stage_rows_in(s_sh, shs + goff, cnt, row, tid, PB_THREADS);
     for (int i = tid; i < PB_THREADS * rowp; i += PB_THREADS) s_dsh[i] = 0.f;
     __syncthreads();
 
     const int idx = base + tid;
-    const bool live = idx < N;
+    const bool live = idx < first + count;
     GaussAcc A;
     float dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     bool any_vis = false;
@@ -361,8 +362,10 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
                                         float scale_modifier, int N, int M, const float* means3D, const float* shs,
                                         const float* scales, const float* rotations, const int32_t* radii,
                                         const SplatGrad* sg, float* dmeans3D, float* dmeans2D, float* dshs,
-                                        float* dopac, float* dscales, float* drots, int accumulate, cudaStream_t s) {
-    if (N <= 0 || V <= 0) return 0;
+                                        float* dopac, float* dscales, float* drots, int accumulate, int first, int count,
+                                        cudaStream_t s) {
+    if (N <= 0 || V <= 0 || count <= 0) return 0;
+    if (first % PB_THREADS) { gs_set_error("preprocess_backward_multi: range start must be a multiple of %d", PB_THREADS); return 1; }
     if (V > PB_MAXV) { gs_set_error("preprocess_backward_multi: V=%d > %d", V, PB_MAXV); return 1; }
     size_t smem = 2 * (size_t)PB_THREADS * ((3 * M) | 1) * sizeof(float);
     static bool attr_set = false;
@@ -370,10 +373,11 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
         GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_backward_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    int blocks = (N + PB_THREADS - 1) / PB_THREADS;
+    int blocks = (count + PB_THREADS - 1) / PB_THREADS;
     preprocess_backward_multi_kernel<<<blocks, PB_THREADS, smem, s>>>(views_dev, V, W, H, sh_degree, scale_modifier, N, M,
                                                                       means3D, shs, scales, rotations, radii, sg, dmeans3D,
-                                                                      dmeans2D, dshs, dopac, dscales, drots, accumulate);
+                                                                      dmeans2D, dshs, dopac, dscales, drots, accumulate, first,
+                                                                      count);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -447,8 +447,8 @@ void* slot_alloc_cb(void* user, int32_t tag, size_t bytes) { return ((Slot*)user
 struct StepCache {
     Slot slot[2];
     bool init = false;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t evFork = nullptr, evPB = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr;
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
     Region ws_recs, ws_sg, ws_u32;               // per-chunk [VB][N] arrays of the multi-view step
@@ -461,6 +461,8 @@ struct StepCache {
             GS_CUDA_CHECK(cudaHostAlloc((void**)&slot[i].host_total, 64, cudaHostAllocDefault));
         }
         GS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        GS_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evD2H, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evPB, cudaEventDisableTiming));
         init = true;
@@ -482,10 +484,14 @@ PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
 // (parameters read once), then per view [depth sort -> scan -> (host: pair count) -> emit -> tile sort ->
 // ranges -> composite fwd -> composite bwd] pipelined over the two slot streams, then ONE multi-view
 // preprocess-backward pass (parameters read once, gradients written once).
+// grad_sink (optional): called after each Gaussian range [first, first+count) of the FINAL preprocess-backward has
+// been enqueued on `user`, so a host-buffer caller can start the D2H of that range while the next one computes.
+struct GradSink { void (*fn)(void* ctx, int first, int count, cudaStream_t user); void* ctx; int nchunks; };
+
 int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const float* views_host,
               const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
               const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
-              cudaStream_t user) {
+              cudaStream_t user, const GradSink* sink = nullptr) {
     StepCache& C = g_step;
     if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
@@ -568,10 +574,18 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
         }
         if (rc) break;
-        { StageTimer t(8, user);
-        rc = gs_launch_preprocess_backward_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M,
-                                                 par.means, par.shs, par.scales, par.rots, radii_all, sg_all, grd.means,
-                                                 grd.m2d, grd.shs, grd.opac, grd.scales, grd.rots, v0 > 0 ? 1 : 0, user); }
+        const bool last_chunk = v0 + VB >= V;
+        const int nparts = (sink && last_chunk && sink->nchunks > 1) ? sink->nchunks : 1;
+        const int per = (((N + nparts - 1) / nparts) + 127) / 128 * 128;
+        for (int first = 0; first < N && !rc; first += per) {
+            const int count = std::min(per, N - first);
+            { StageTimer t(8, user);
+            rc = gs_launch_preprocess_backward_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M,
+                                                     par.means, par.shs, par.scales, par.rots, radii_all, sg_all, grd.means,
+                                                     grd.m2d, grd.shs, grd.opac, grd.scales, grd.rots, v0 > 0 ? 1 : 0, first,
+                                                     count, user); }
+            if (!rc && sink && last_chunk) sink->fn(sink->ctx, first, count, user);
+        }
     }
     if (num_rendered_out) *num_rendered_out = rendered;
     return rc;
@@ -603,26 +617,47 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     while ((int)C.up_ready.size() < V) {
         cudaEvent_t e; GS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); C.up_ready.push_back(e);
     }
-    // upstream gradients stream in on the copy engine, view by view, behind the compute
+    // H2D order on the copy stream: parameters FIRST (compute cannot start without them), then the upstream
+    // gradients view by view (needed only at each view's backward), so they stream in behind the compute.
     GS_CUDA_CHECK(cudaEventRecord(C.evFork, s));
     GS_CUDA_CHECK(cudaStreamWaitEvent(C.copy_stream, C.evFork, 0));
+    GS_CUDA_CHECK(cudaMemcpyAsync(d_views, views_host, (size_t)V * 160, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.means, means3D_host, (size_t)N * 12, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.opac, opacities_host, (size_t)N * 4, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.scales, scales_host, (size_t)N * 12, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.rots, rotations_host, (size_t)N * 16, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaMemcpyAsync(par.shs, shs_host, (size_t)N * 12 * M, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaEventRecord(C.evPB, C.copy_stream));
     for (int v = 0; v < V; v++) {
         GS_CUDA_CHECK(cudaMemcpyAsync(d_up + (size_t)v * 5 * npix, dL_dout_host + (size_t)v * 5 * npix, 5 * npix * 4,
                                       cudaMemcpyHostToDevice, C.copy_stream));
         GS_CUDA_CHECK(cudaEventRecord(C.up_ready[v], C.copy_stream));
     }
-    GS_CUDA_CHECK(cudaMemcpyAsync(par.means, means3D_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(par.opac, opacities_host, (size_t)N * 4, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(par.scales, scales_host, (size_t)N * 12, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(par.rots, rotations_host, (size_t)N * 16, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(d_views, views_host, (size_t)V * 160, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaMemcpyAsync(par.shs, shs_host, (size_t)N * 12 * M, cudaMemcpyHostToDevice, s));
+    GS_CUDA_CHECK(cudaStreamWaitEvent(s, C.evPB, 0));
+    // D2H of the summed gradients is chunked over Gaussian ranges and starts as soon as a range is final
+    struct SinkCtx { StepCache* C; float* host; float* dev; size_t N, M; } sctx{&C, grads_host, d_grad, (size_t)N, (size_t)M};
+    GradSink sink;
+    sink.ctx = &sctx; sink.nchunks = grads_host ? 4 : 1;
+    sink.fn = [](void* vp, int first, int count, cudaStream_t user) {
+        SinkCtx* q = (SinkCtx*)vp;
+        if (!q->host) return;
+        StepCache& C2 = *q->C;
+        cudaEventRecord(C2.evD2H, user);
+        cudaStreamWaitEvent(C2.d2h_stream, C2.evD2H, 0);
+        const size_t n = q->N, M2 = q->M;
+        const size_t goff[6] = {0, 3 * n, 3 * n + 3 * M2 * n, 3 * n + 3 * M2 * n + n, 3 * n + 3 * M2 * n + 4 * n, 3 * n + 3 * M2 * n + 8 * n};
+        const size_t per[6] = {3, 3 * M2, 1, 3, 4, 3};          // means | shs | opac | scales | rots | means2D
+        for (int gI = 0; gI < 6; gI++) {
+            const size_t off = goff[gI] + (size_t)first * per[gI];
+            cudaMemcpyAsync(q->host + off, q->dev + off, (size_t)count * per[gI] * 4, cudaMemcpyDeviceToHost, C2.d2h_stream);
+        }
+    };
     GS_CUDA_CHECK(cudaMemsetAsync(d_grad, 0, n_grad * 4, s));
     if (step_core(V, H, W, sh_degree, scale_modifier, views_host, d_views, N, M, par, d_up, C.up_ready.data(), grd,
-                  d_img, num_rendered_out, s)) return 1;
+                  d_img, num_rendered_out, s, &sink)) return 1;
     if (grads_dev) GS_CUDA_CHECK(cudaMemcpyAsync(grads_dev, d_grad, n_grad * 4, cudaMemcpyDeviceToDevice, s));
-    if (grads_host) GS_CUDA_CHECK(cudaMemcpyAsync(grads_host, d_grad, n_grad * 4, cudaMemcpyDeviceToHost, s));
     if (images_host) GS_CUDA_CHECK(cudaMemcpyAsync(images_host, d_img, (size_t)V * 5 * npix * 4, cudaMemcpyDeviceToHost, s));
+    if (grads_host) GS_CUDA_CHECK(cudaStreamSynchronize(C.d2h_stream));
     if (grads_host || images_host) GS_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
 }

@@ -157,7 +157,8 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
                                         float scale_modifier, int N, int M, const float* means3D, const float* shs,
                                         const float* scales, const float* rotations, const int32_t* radii,
                                         const SplatGrad* sg, float* dmeans3D, float* dmeans2D, float* dshs,
-                                        float* dopac, float* dscales, float* drots, int accumulate, cudaStream_t s);
+                                        float* dopac, float* dscales, float* drots, int accumulate, int first, int count,
+                                        cudaStream_t s);
 
 int gs_launch_activate(int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gs_launch_adam(int, int, const float*, float, float, float, int, float, const float*, float*, float*, float*, cudaStream_t);
