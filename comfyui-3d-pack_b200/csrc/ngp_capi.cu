@@ -17,6 +17,10 @@ int ngp_weights_bwd(const float*, const float*, const int32_t*, long long, const
 int ngp_accumulate_fwd(const float*, const float*, int, const int32_t*, long long, float*, cudaStream_t);
 int ngp_accumulate_bwd(const float*, const float*, int, const long long*, long long, const float*, float*, float*, cudaStream_t);
 
+int ngp_mlp2_supported(int, int, int);
+int ngp_mlp2_fwd(const float*, long long, int, int, int, const float*, const float*, float*, cudaStream_t);
+int ngp_mlp2_bwd(const float*, long long, int, int, int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+
 #define NGP_REQ(cond, msg) do { if (!(cond)) { gs_set_error("%s: %s", __func__, msg); return 1; } } while (0)
 
 extern "C" {
@@ -77,5 +81,18 @@ int32_t ngp_b200_accumulate_bwd(const float* w, const float* v, int32_t C, const
                                 float* dw, float* dv, void* stream) {
     NGP_REQ(S == 0 || (w && ri && g_out && dw), "NULL pointer");
     return ngp_accumulate_bwd(w, v, C, (const long long*)ri, S, g_out, dw, dv, (cudaStream_t)stream);
+}
+int32_t ngp_b200_mlp2_supported(int32_t Din, int32_t H, int32_t Dout) { return ngp_mlp2_supported(Din, H, Dout); }
+int32_t ngp_b200_mlp2_fwd(const float* X, int64_t N, int32_t Din, int32_t H, int32_t Dout, const float* W1, const float* W2,
+                          float* Y, void* stream) {
+    NGP_REQ(N == 0 || (X && W1 && W2 && Y), "NULL pointer");
+    NGP_REQ(((size_t)X & 15) == 0, "X must be 16-byte aligned");
+    return ngp_mlp2_fwd(X, N, Din, H, Dout, W1, W2, Y, (cudaStream_t)stream);
+}
+int32_t ngp_b200_mlp2_bwd(const float* X, int64_t N, int32_t Din, int32_t H, int32_t Dout, const float* W1, const float* W2,
+                          const float* GY, float* GX, float* GW1, float* GW2, void* stream) {
+    NGP_REQ(N == 0 || (X && W1 && W2 && GY && GW1 && GW2), "NULL pointer");
+    NGP_REQ(((size_t)X & 15) == 0 && ((size_t)GX & 15) == 0, "X/GX must be 16-byte aligned");
+    return ngp_mlp2_bwd(X, N, Din, H, Dout, W1, W2, GY, GX, GW1, GW2, (cudaStream_t)stream);
 }
 }

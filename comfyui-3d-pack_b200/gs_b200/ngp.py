@@ -111,8 +111,37 @@ class GridEncoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ kiui.nn / kiui.op / kiui.cam
+class _FusedMLP2(torch.autograd.Function):
+    """y = W2 relu(W1 x): one pass, hidden layer in registers (ngp_mlp.cu); backward recomputes it."""
+
+    @staticmethod
+    def forward(ctx, x, W1, W2):
+        xs, w1, w2 = _f32c(x), _f32c(W1), _f32c(W2)
+        N, Din = xs.shape
+        H, Dout = w1.shape[0], w2.shape[0]
+        y = torch.empty(N, Dout, device=xs.device)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib.ngp_b200_mlp2_fwd(_P(xs), N, Din, H, Dout, _P(w1), _P(w2), _P(y), _stream()))
+        ctx.save_for_backward(xs, w1, w2)
+        ctx.need_gx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xs, w1, w2 = ctx.saved_tensors
+        N, Din = xs.shape
+        H, Dout = w1.shape[0], w2.shape[0]
+        g = _f32c(gy)
+        gx = torch.empty_like(xs) if ctx.need_gx else None
+        gw1 = torch.zeros_like(w1); gw2 = torch.zeros_like(w2)
+        with torch.cuda.device(xs.device):
+            _lib.check(_lib.lib.ngp_b200_mlp2_bwd(_P(xs), N, Din, H, Dout, _P(w1), _P(w2), _P(g), _P(gx), _P(gw1), _P(gw2), _stream()))
+        return gx, gw1, gw2
+
+
 class MLP(nn.Module):
-    """kiui.nn.MLP: Linear(+ReLU) stack."""
+    """kiui.nn.MLP: Linear(+ReLU) stack.  The 2-layer, bias-free, hidden-32 shape the reference uses
+    (Instant_NGP.py:34-35) runs as ONE fused kernel; any other shape uses torch Linear (library GEMM)."""
 
     def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True):
         super().__init__()
@@ -120,7 +149,13 @@ class MLP(nn.Module):
         self.net = nn.ModuleList([nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=bias)
                                   for l in range(num_layers)])
 
+    def _fusable(self, x):
+        return (self.num_layers == 2 and self.net[0].bias is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+                and x.shape[0] > 0 and _lib.lib.ngp_b200_mlp2_supported(self.dim_in, self.dim_hidden, self.dim_out))
+
     def forward(self, x):
+        if self._fusable(x):
+            return _FusedMLP2.apply(x, self.net[0].weight, self.net[1].weight)
         for l in range(self.num_layers):
             x = self.net[l](x)
             if l != self.num_layers - 1:

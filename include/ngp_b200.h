@@ -56,6 +56,15 @@ int32_t ngp_b200_accumulate_fwd(const float* weights, const float* values, int32
                                 int64_t n_rays, float* out, void* stream);
 int32_t ngp_b200_accumulate_bwd(const float* weights, const float* values, int32_t C, const int64_t* ray_indices,
                                 int64_t S, const float* g_out, float* d_weights, float* d_values, void* stream);
+/* ---- fused tiny MLP: y = W2 relu(W1 x), no bias (kiui.nn.MLP(dim_in, dim_out, 32, 2, bias=False), Instant_NGP.py:34-35)
+ * X[N,Din], W1[H,Din], W2[Dout,H] (torch Linear weight layout), Y[N,Dout].  Supported: H=32, Din in {24,32}, Dout 1..4
+ * (ngp_b200_mlp2_supported); other shapes stay on the library GEMM path in the host wrapper.
+ * Backward: GX[N,Din] written (may be NULL), GW1/GW2 ADDED to (caller zeroes). */
+int32_t ngp_b200_mlp2_supported(int32_t Din, int32_t H, int32_t Dout);
+int32_t ngp_b200_mlp2_fwd(const float* X, int64_t N, int32_t Din, int32_t H, int32_t Dout, const float* W1, const float* W2,
+                          float* Y, void* stream);
+int32_t ngp_b200_mlp2_bwd(const float* X, int64_t N, int32_t Din, int32_t H, int32_t Dout, const float* W1, const float* W2,
+                          const float* GY, float* GX, float* GW1, float* GW2, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -169,3 +169,24 @@ def test_occupancy_grid_update_host_logic(dev):
     est.update_every_n_steps(3, occ_eval_fn=ball, occ_thre=0.01, n=8)        # not a multiple of n: no-op
     est.update_every_n_steps(512, occ_eval_fn=ball, occ_thre=0.01, n=8)      # post-warm-up branch
     assert bool(est.binaries[0][inside].all())
+
+
+@pytest.mark.parametrize("din,dout,n", [(24, 1, 1000), (24, 3, 4097), (32, 1, 70000), (32, 3, 128), (32, 4, 333)])
+def test_fused_mlp_matches_linear_stack(dev, din, dout, n):
+    from kiui.nn import MLP
+    torch.manual_seed(din + dout)
+    m = MLP(din, dout, 32, 2, bias=False).to(dev)
+    x = torch.randn(n, din, device=dev)
+    xr = x.clone().requires_grad_(True); xf = x.clone().requires_grad_(True)
+    ref = torch.relu(xr @ m.net[0].weight.T) @ m.net[1].weight.T
+    out = m(xf)                                                   # fused path
+    assert out.shape == (n, dout) and float((out - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    g = torch.randn(n, dout, device=dev)
+    gw_ref = torch.autograd.grad((ref * g).sum(), [xr, m.net[0].weight, m.net[1].weight])
+    gw = torch.autograd.grad((out * g).sum(), [xf, m.net[0].weight, m.net[1].weight])
+    for a, b in zip(gw, gw_ref):
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-4
+    # shapes the fused kernel does not cover fall back to the Linear stack
+    m2 = MLP(16, 2, 64, 3, bias=True).to(dev)
+    assert m2(torch.randn(10, 16, device=dev)).shape == (10, 2)
+    assert m(x.view(10, -1, din)).shape[-1] == dout if n % 10 == 0 else True
