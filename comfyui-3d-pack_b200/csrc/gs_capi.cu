@@ -154,6 +154,21 @@ unsigned long long* pinned_u64() {
 extern "C" {
 
 int32_t gs_b200_abi_version(void) { return GS_B200_ABI_VERSION; }
+
+// tile culling mode: 0 = off (the package's tile lists everywhere), 1 = multi-view step entries only (default),
+// 2 = also gs_b200_rasterize_forward.  Images are bit-identical in every mode; see tight_spans() in gs_preprocess.cu.
+static int tile_culling_init() {
+    const char* e = getenv("GS_B200_TILE_CULLING");
+    if (e && *e) { int v = atoi(e); return v < 0 ? 0 : (v > 2 ? 2 : v); }
+    return 1;
+}
+static std::atomic<int> g_tile_culling{tile_culling_init()};
+int32_t gs_b200_set_tile_culling(int32_t mode) {
+    if (mode < 0 || mode > 2) { gs_set_error("tile culling mode must be 0, 1 or 2"); return 1; }
+    g_tile_culling.store(mode);
+    return 0;
+}
+int32_t gs_b200_get_tile_culling(void) { return g_tile_culling.load(); }
 int64_t gs_b200_launch_count(void) { return (int64_t)g_launches.load(); }
 void gs_b200_profile_enable(int32_t on) {
     std::lock_guard<std::mutex> l(g_prof_mu);
@@ -195,6 +210,7 @@ struct FwdCtx {
     gs_b200_state* state = nullptr;
     SplatRec* recs = nullptr;
     uint32_t *sorted_ids = nullptr, *offsets = nullptr;
+    uint4* spans = nullptr;                        // tile culling: per-row tile spans (NULL = full squares)
     unsigned long long* host_total = nullptr;      // pinned
     float *out_color = nullptr, *out_depth = nullptr, *out_alpha = nullptr;
     cudaStream_t s = nullptr;
@@ -202,7 +218,7 @@ struct FwdCtx {
 };
 
 // per-view arrays already produced by the multi-view preprocess (gs_launch_preprocess_multi)
-struct PreView { SplatRec* recs; uint32_t *tiles, *dkeys, *ids, *min_key; };
+struct PreView { SplatRec* recs; uint32_t *tiles, *dkeys, *ids, *min_key; uint4* spans; };
 
 static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
                        const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
@@ -238,10 +254,13 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
     *host_total = 0;
     if (N > 0) {
         const size_t sort_b = gs_sort_scratch_bytes(N), scan_b = gs_scan_scratch_bytes(N);
-        const size_t sc_bytes = Carver::need(N, 4) * 6 + Carver::need(1, 8) * 2 + Carver::need(sort_b, 1) + Carver::need(scan_b, 1);
+        const bool own_spans = !pre && g_tile_culling.load() == 2;
+        const size_t sc_bytes = Carver::need(N, 4) * 6 + Carver::need(1, 8) * 2 + Carver::need(sort_b, 1) + Carver::need(scan_b, 1) +
+                                (own_spans ? Carver::need(N, 16) : 0);
         void* sc = A.get(GS_B200_BUF_SCRATCH, sc_bytes);
         if (A.failed) return 1;
         Carver cv(sc);
+        c.spans = pre ? pre->spans : (own_spans ? cv.take<uint4>(N) : nullptr);
         uint32_t* tiles = cv.take<uint32_t>(N);
         uint32_t* dkeys = cv.take<uint32_t>(N);
         uint32_t* ids = cv.take<uint32_t>(N);
@@ -256,7 +275,7 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
         void* scan_scratch = cv.take<char>(scan_b);
         { StageTimer t(0, s);
         if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 c.recs, radii, tiles, dkeys, ids, min_key, s)) return 1; }
+                                 c.recs, radii, tiles, dkeys, ids, min_key, c.spans, s)) return 1; }
         STAGE_CHECK(c.dbg, s, "preprocess");
         int in_alt = 0;
         { StageTimer t(1, s);
@@ -300,7 +319,7 @@ static int fwd_phase_b(FwdCtx& c) {
         uint32_t *k0 = (npasses & 1) ? keys_b : state->tile_keys, *v0 = (npasses & 1) ? vals_b : state->point_list;
         uint32_t *k1 = (npasses & 1) ? state->tile_keys : keys_b, *v1 = (npasses & 1) ? state->point_list : vals_b;
         { StageTimer t(3, s);
-        if (gs_launch_emit(c.recs, c.sorted_ids, c.offsets, c.N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1; }
+        if (gs_launch_emit(c.recs, c.spans, c.sorted_ids, c.offsets, c.N, va.tiles_x, va.tiles_y, k0, v0, s)) return 1; }
         STAGE_CHECK(c.dbg, s, "emit");
         int in_alt = 0;
         { StageTimer t(4, s);
@@ -451,7 +470,7 @@ struct StepCache {
     cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr;
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
-    Region ws_recs, ws_sg, ws_u32;               // per-chunk [VB][N] arrays of the multi-view step
+    Region ws_recs, ws_sg, ws_u32, ws_spans;               // per-chunk [VB][N] arrays of the multi-view step
     int ensure_init() {
         if (init) return 0;
         for (int i = 0; i < 2; i++) {
@@ -500,6 +519,9 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     const size_t nvb = (size_t)VB * N;
     if (Slot::ensure(C.ws_recs, nvb * sizeof(SplatRec), user) || Slot::ensure(C.ws_sg, nvb * sizeof(SplatGrad), user) ||
         Slot::ensure(C.ws_u32, nvb * 4 * 4 + 256 * 4, user)) return 1;
+    const bool tight = g_tile_culling.load() >= 1;
+    if (tight && Slot::ensure(C.ws_spans, nvb * sizeof(uint4), user)) return 1;
+    uint4* spans_all = tight ? (uint4*)C.ws_spans.p : nullptr;
     SplatRec* recs_all = (SplatRec*)C.ws_recs.p;
     SplatGrad* sg_all = (SplatGrad*)C.ws_sg.p;
     uint32_t* u32 = (uint32_t*)C.ws_u32.p;
@@ -522,7 +544,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
         { StageTimer t(0, user);
         if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
                                        par.shs, par.opac, par.scales, par.rots, recs_all, radii_all, tiles_all,
-                                       dkeys_all, ids_all, minkeys, user)) return 1; }
+                                       dkeys_all, ids_all, minkeys, spans_all, user)) return 1; }
         // fork: both slot streams continue after the preprocess
         GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
         for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evFork, 0));
@@ -542,7 +564,8 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             delete ctx[j & 1];
             ctx[j & 1] = new FwdCtx(slot_alloc_cb, &S, S.stream);
             const size_t o = (size_t)j * N;
-            PreView pre{recs_all + o, tiles_all + o, dkeys_all + o, ids_all + o, minkeys + 2 * j};
+            PreView pre{recs_all + o, tiles_all + o, dkeys_all + o, ids_all + o, minkeys + 2 * j,
+                        spans_all ? spans_all + o : nullptr};
             if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
                             img, img + 3 * npix, img + 4 * npix, radii_all + o, &st[j & 1], S.host_total, &pre)) return 1;
             GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));

@@ -138,7 +138,7 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
                          const float* colors_precomp, const float* opacities, const float* scales,
                          const float* rotations, const float* cov3D_precomp, SplatRec* recs, int32_t* radii,
                          uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_key,
-                         cudaStream_t s);
+                         uint4* spans /* NULL = the package's full 3-sigma square */, cudaStream_t s);
 
 int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float* means3D, const float* shs,
                                   const float* colors_precomp, const float* opacities, const float* scales,
@@ -152,7 +152,7 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
                                int M, const float* means3D, const float* shs, const float* opacities,
                                const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
                                uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
-                               cudaStream_t s);
+                               uint4* spans, cudaStream_t s);
 int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, int H, int sh_degree,
                                         float scale_modifier, int N, int M, const float* means3D, const float* shs,
                                         const float* scales, const float* rotations, const int32_t* radii,
@@ -177,7 +177,7 @@ size_t gs_scan_scratch_bytes(int64_t n);
 int gs_scan_gather_u32(const uint32_t* tiles, const uint32_t* ids, uint32_t* offsets, unsigned long long* total,
                        int64_t n, void* scratch, cudaStream_t s);
 
-int gs_launch_emit(const SplatRec* recs, const uint32_t* sorted_ids, const uint32_t* offsets, int N,
+int gs_launch_emit(const SplatRec* recs, const uint4* spans, const uint32_t* sorted_ids, const uint32_t* offsets, int N,
                    int tiles_x, int tiles_y, uint32_t* tile_keys, uint32_t* vals, cudaStream_t s);
 int gs_launch_ranges(const uint32_t* sorted_tile_keys, int64_t P, uint32_t* ranges, cudaStream_t s);
 

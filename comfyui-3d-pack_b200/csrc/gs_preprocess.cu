@@ -86,17 +86,67 @@ __device__ __forceinline__ void cov3d_of(const float* __restrict__ scales, const
     c[5] = M20 * M20 + M21 * M21 + M22 * M22;
 }
 
+// Optional tight tile list ("tile culling").  The package lists every tile of the 3-sigma bounding square; most of
+// those (tile, splat) pairs cannot reach alpha >= 1/255 anywhere in the tile and only cost sort / staging work.
+// Here the exact level set  q(u) = 0.5(A ux^2 + C uy^2) + B ux uy <= log2(255 o)  (log2-scaled conic, same
+// conservative slack as the composite's sub-rect mask) is intersected with each tile row of the square:
+// x-extent of the ellipse inside the row's y-strip -> a span of tiles.  Result: 8 rows x (start-x0 | count<<8)
+// packed in a uint4, or spans.x = 0xFFFFFFFF for "whole square" (big squares, degenerate conics).
+// Pruned pairs contribute to no pixel, so images are bit-identical; only list positions (n_contrib) shift.
+__device__ __forceinline__ void tight_spans(float px, float py, const float4 cq, int x0, int y0, int x1, int y1,
+                                            uint32_t& count, uint4& spans) {
+    spans = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+    const int w = x1 - x0, h = y1 - y0;
+    if (w > 255 || h > 8) return;
+    const float o = cq.w;
+    if (!(o * 255.0f >= 1.0f)) { count = 0; spans = make_uint4(0u, 0u, 0u, 0u); return; }
+    const float tau = log2f(o * 255.0f) * 1.001f + 0.03f;
+    const float A = -2.0f * cq.x, B = -cq.y, C = -2.0f * cq.z;
+    const float det = A * C - B * B;
+    if (!(A > 0.f && det > 0.f)) return;
+    const float inv_det = 1.0f / det, invA = 1.0f / A;
+    const float k2 = 2.0f * tau * A;
+    const float Ymax = sqrtf(k2 * inv_det), Xmax = sqrtf(2.0f * tau * C * inv_det);
+    const float uyR = -(B * Xmax) / C;                      // y offset of the right-most point of the ellipse
+    if (!(isfinite(Ymax) && isfinite(Xmax) && isfinite(uyR) && isfinite(px) && isfinite(py))) return;
+    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    uint32_t total = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        uint32_t cnt = 0, start = 0;
+        if (r < h) {
+            const float a = (float)((y0 + r) * GS_TILE) - py, b = a + (float)(GS_TILE - 1);
+            const float lo = fmaxf(a, -Ymax), hi = fminf(b, Ymax);
+            if (lo <= hi) {
+                const float yr = fminf(fmaxf(uyR, lo), hi), yl = fminf(fmaxf(-uyR, lo), hi);
+                float xr = (-(B * yr) + sqrtf(fmaxf(k2 - det * yr * yr, 0.f))) * invA;
+                float xl = (-(B * yl) - sqrtf(fmaxf(k2 - det * yl * yl, 0.f))) * invA;
+                xr += 0.01f + 1e-4f * fabsf(xr);
+                xl -= 0.01f + 1e-4f * fabsf(xl);
+                const int ta = max(x0, (int)ceilf((px + xl - (float)(GS_TILE - 1)) * (1.0f / GS_TILE)));
+                const int tb = min(x1 - 1, (int)floorf((px + xr) * (1.0f / GS_TILE)));
+                if (tb >= ta) { cnt = (uint32_t)(tb - ta + 1); start = (uint32_t)(ta - x0); }
+            }
+        }
+        packed[r >> 1] |= (start | (cnt << 8)) << (16 * (r & 1));
+        total += cnt;
+    }
+    count = total;
+    spans = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
 // View-dependent part for one Gaussian: cull, project, EWA cov2D, extent, rect, colour -> record.
 __device__ __forceinline__ void project_view(const ViewK& vk, int deg, int M, float x, float y, float z,
                                              const float c[6], float opacity, const float* __restrict__ sh_row,
                                              const float* __restrict__ col, SplatRec& rec, int& my_radius,
-                                             uint32_t& tiles, uint32_t& dkey) {
+                                             uint32_t& tiles, uint32_t& dkey, bool tight, uint4& spans) {
     const float* m = vk.m;
     const float* p = vk.p;
     rec.g = make_float4(0.f, 0.f, 0.f, 0.f);
     rec.c = make_float4(0.f, 0.f, 0.f, 0.f);
     rec.k = make_float4(0.f, 0.f, 0.f, 0.f);
     my_radius = 0; tiles = 0; dkey = 0xFFFFFFFFu;
+    spans = make_uint4(0u, 0u, 0u, 0u);
     const float tx = m[0] * x + m[4] * y + m[8] * z + m[12];
     const float ty = m[1] * x + m[5] * y + m[9] * z + m[13];
     const float tz = m[2] * x + m[6] * y + m[10] * z + m[14];
@@ -149,6 +199,7 @@ __device__ __forceinline__ void project_view(const ViewK& vk, int deg, int M, fl
     // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
     const float L2E = 1.4426950408889634f;
     rec.c = make_float4(-0.5f * L2E * (cc * det_inv), L2E * (cb * det_inv), -0.5f * L2E * (ca * det_inv), opacity);
+    if (tight) tight_spans(px, py, rec.c, x0, y0, x1, y1, tiles, spans);
     rec.k = make_float4(cr, cg, cbl, __uint_as_float(tiles));
 }
 
@@ -161,7 +212,8 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
                   const float* __restrict__ scales, const float* __restrict__ rotations,
                   const float* __restrict__ cov3D_precomp, SplatRec* __restrict__ recs,
                   int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, uint32_t* __restrict__ min_key) {
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, uint32_t* __restrict__ min_key,
+                  uint4* __restrict__ spans) {
     extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_view[16], s_proj[16], s_cam[3];
     __shared__ uint32_t s_min;
@@ -182,10 +234,12 @@ preprocess_kernel(ViewArgs va, int N, int M, const float* __restrict__ means3D, 
     float c[6];
     cov3d_of(scales, rotations, cov3D_precomp, va.scale_modifier, idx, c);
     ViewK vk{s_view, s_proj, s_cam, va.tanfovx, va.tanfovy, va.focal_x, va.focal_y, va.W, va.H, va.tiles_x, va.tiles_y};
-    SplatRec rec; int my_radius; uint32_t tiles, dkey;
+    SplatRec rec; int my_radius; uint32_t tiles, dkey; uint4 sp;
     project_view(vk, va.sh_degree, M, x, y, z, c, opacities[idx], s_sh + (idx - base) * rowp,
-                 colors_precomp ? colors_precomp + 3 * (size_t)idx : nullptr, rec, my_radius, tiles, dkey);
+                 colors_precomp ? colors_precomp + 3 * (size_t)idx : nullptr, rec, my_radius, tiles, dkey,
+                 spans != nullptr, sp);
     if (live) {
+        if (spans) spans[idx] = sp;
         recs[idx] = rec;
         radii[idx] = my_radius;
         tiles_touched[idx] = tiles;
@@ -209,7 +263,7 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
                         const float* __restrict__ rotations, SplatRec* __restrict__ recs,
                         int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
                         uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids,
-                        uint32_t* __restrict__ min_keys /* [V] stride 2 words */) {
+                        uint32_t* __restrict__ min_keys /* [V] stride 2 words */, uint4* __restrict__ spans) {
     extern __shared__ __align__(16) float s_sh[];
     __shared__ float s_views[PP_MAXV * 40];
     __shared__ uint32_t s_min[PP_MAXV];
@@ -232,10 +286,12 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
         const float* vw = s_views + v * 40;
         const float tfx = vw[38], tfy = vw[39];
         ViewK vk{vw, vw + 16, vw + 32, tfx, tfy, (float)W / (2.0f * tfx), (float)H / (2.0f * tfy), W, H, tiles_x, tiles_y};
-        SplatRec rec; int my_radius; uint32_t tiles, dkey;
-        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, nullptr, rec, my_radius, tiles, dkey);
+        SplatRec rec; int my_radius; uint32_t tiles, dkey; uint4 sp;
+        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, nullptr, rec, my_radius, tiles, dkey,
+                     spans != nullptr, sp);
         if (live) {
             const size_t o = (size_t)v * N + idx;
+            if (spans) spans[o] = sp;
             recs[o] = rec;
             radii[o] = my_radius;
             tiles_touched[o] = tiles;
@@ -254,7 +310,7 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
                          const float* colors_precomp, const float* opacities, const float* scales,
                          const float* rotations, const float* cov3D_precomp, SplatRec* recs, int32_t* radii,
                          uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_key,
-                         cudaStream_t s) {
+                         uint4* spans, cudaStream_t s) {
     if (N <= 0) return 0;
     size_t smem = shs ? (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float) : 0;
     if (smem > 48 * 1024) {
@@ -263,7 +319,7 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
     int blocks = (N + PP_THREADS - 1) / PP_THREADS;
     preprocess_kernel<<<blocks, PP_THREADS, smem, s>>>(va, N, M, means3D, shs, colors_precomp, opacities, scales,
                                                        rotations, cov3D_precomp, recs, radii, tiles_touched,
-                                                       depth_keys, ids, min_key);
+                                                       depth_keys, ids, min_key, spans);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -275,7 +331,7 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
                                int M, const float* means3D, const float* shs, const float* opacities,
                                const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
                                uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
-                               cudaStream_t s) {
+                               uint4* spans, cudaStream_t s) {
     if (N <= 0 || V <= 0) return 0;
     if (V > PP_MAXV) { gs_set_error("preprocess_multi: V=%d > %d", V, PP_MAXV); return 1; }
     size_t smem = (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float);
@@ -284,7 +340,7 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
     int blocks = (N + PP_THREADS - 1) / PP_THREADS;
     preprocess_multi_kernel<<<blocks, PP_THREADS, smem, s>>>(views_dev, V, W, H, sh_degree, scale_modifier, N, M, means3D,
                                                              shs, opacities, scales, rotations, recs, radii,
-                                                             tiles_touched, depth_keys, ids, min_keys);
+                                                             tiles_touched, depth_keys, ids, min_keys, spans);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -242,6 +242,17 @@ def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_pre
     return out
 
 
+def set_tile_culling(mode: int) -> None:
+    """0: the package's tile lists everywhere; 1 (default): culled lists in the multi-view step entries only;
+    2: culled lists in `GaussianRasterizer` too.  Images are bit-identical in all modes (include/gs_b200.h)."""
+    if _lib.lib.gs_b200_set_tile_culling(int(mode)) != 0:
+        raise ValueError(_lib.last_error())
+
+
+def get_tile_culling() -> int:
+    return int(_lib.lib.gs_b200_get_tile_culling())
+
+
 def sort_pairs_u32(keys: torch.Tensor, vals: Optional[torch.Tensor], begin_bit: int = 0, end_bit: int = 32):
     """CUB-free onesweep radix sort of int32-viewed u32 keys (+values); returns sorted (keys, vals)."""
     assert keys.is_cuda and keys.dtype == torch.int32 and keys.is_contiguous()

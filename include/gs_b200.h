@@ -83,6 +83,15 @@ typedef struct gs_b200_state {
 int32_t gs_b200_abi_version(void);
 const char* gs_b200_last_error(void);
 
+/* Tile culling (no reference counterpart; an optimisation the caller can switch off).  The package's binning lists
+ * every tile of each splat's 3-sigma bounding square (duplicateWithKeys); with culling on, tiles in which the
+ * splat cannot reach alpha >= 1/255 at any pixel are left out of the list.  Rendered images are bit-identical and
+ * gradients equal up to summation order; only point_list / ranges / n_contrib (list positions) differ from the
+ * package's.  mode 0: off everywhere; 1 (default): gs_b200_step_* entries only; 2: also rasterize_forward.
+ * Initial value can be set with the environment variable GS_B200_TILE_CULLING. */
+int32_t gs_b200_set_tile_culling(int32_t mode);
+int32_t gs_b200_get_tile_culling(void);
+
 /* Forward — replaces `_C.rasterize_gaussians` as called from
  * GaussianRasterizer.forward (main_3DGS_renderer.py:927-936).
  *   M        number of SH coefficients per channel in `shs` ([N,M,3]); ignored when colors_precomp != NULL

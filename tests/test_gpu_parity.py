@@ -227,20 +227,86 @@ def test_multiview_step_entries_agree_with_per_view_path(dev):
     dl_cpu = torch.rand(V, 5, H, W, generator=torch.Generator().manual_seed(7)) * 2 - 1
     dl = dl_cpu.to(dev)
     ia = torch.empty(V, 5, H, W, device=dev); ib = torch.empty(V, 5, H, W, device=dev)
-    p1 = optim_step.step_device(params, views, dl, ia); g1 = params.grads.clone()
-    for _ in range(3):
-        p2 = optim_step.step_device_pipelined(params, views, dl, ib); g2 = params.grads.clone()
-        assert p1 == p2 and torch.equal(ia, ib)
-        assert float((g1 - g2).norm() / g1.norm()) < 1e-5          # atomics: summation order differs
-    hs = optim_step.HostStep({k: v.cpu() for k, v in cloud.items()}, vnp, W, H, deg, dl_cpu)
-    for _ in range(2):
-        assert hs.run() == p1
-        assert float((hs.grads.to(dev) - g1).norm() / g1.norm()) < 1e-5
+    from gs_b200 import rasterizer as R
+    assert R.get_tile_culling() == 1
+    p1 = optim_step.step_device(params, views, dl, ia); g1 = params.grads.clone()   # per-view C entries: package lists
+    try:
+        for mode in (0, 1):
+            R.set_tile_culling(mode)
+            for _ in range(3):
+                p2 = optim_step.step_device_pipelined(params, views, dl, ib); g2 = params.grads.clone()
+                assert torch.equal(ia, ib)                             # images bit-identical with and without culling
+                assert (p1 == p2) if mode == 0 else (0 < p2 < p1)
+                assert float((g1 - g2).norm() / g1.norm()) < 1e-5      # atomics: summation order differs
+            hs = optim_step.HostStep({k: v.cpu() for k, v in cloud.items()}, vnp, W, H, deg, dl_cpu)
+            for _ in range(2):
+                assert hs.run() == p2
+                assert float((hs.grads.to(dev) - g1).norm() / g1.norm()) < 1e-5
+    finally:
+        R.set_tile_culling(1)
     # and the packed buffer equals the sum of per-view oracle-checked autograd gradients for one view
     from gs_b200 import rasterizer as R
     cam = camera.MiniCam(camera.orbit_camera(0, 0.0, 1.75), W, H, np.deg2rad(49.1),
                          2 * np.arctan(np.tan(np.deg2rad(49.1) / 2) * W / H), 0.01, 100.0, device=dev)
     assert np.allclose(vnp[0, :16], cam.world_view_transform.reshape(-1).cpu().numpy(), atol=1e-6)
+
+
+# ---------------- tile culling (optional tight tile lists) -----------------------------------------------
+@pytest.mark.parametrize("kind,N,deg,W,H", [("D1", 3000, 2, 200, 120), ("D0", 50000, 3, 640, 360), ("big", 400, 0, 320, 200)])
+def test_tile_culling_is_a_sublist_with_identical_images(R, dev, kind, N, deg, W, H):
+    """Mode 2 drops (tile, splat) pairs that cannot reach alpha >= 1/255 in the tile: the culled list must be an
+    order-preserving sub-list of the package's list per tile, and the images must not change by a single bit."""
+    from gs_b200 import camera, synthetic
+    if kind == "big":       # large, anisotropic splats (squares taller than 8 tiles fall back to the full square)
+        g = torch.Generator().manual_seed(3)
+        cloud = {"means3D": (torch.rand(N, 3, generator=g) - 0.5), "shs": torch.rand(N, 1, 3, generator=g),
+                 "opacities": torch.rand(N, 1, generator=g) ** 3,
+                 "scales": torch.exp(torch.rand(N, 3, generator=g) * 4 - 5), "rotations": torch.randn(N, 4, generator=g)}
+        cloud = {k: v.to(dev).contiguous() for k, v in cloud.items()}
+    else:
+        cloud = synthetic.make_cloud(kind, N, deg, seed=11, device=dev)
+    vnp = camera.orbit_views(3, W, H)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    for v in range(3):
+        rs = R.GaussianRasterizationSettings(H, W, float(vnp[v, 38]), float(vnp[v, 39]), t(vnp[v, 35:38].copy()), 1.0,
+                                            t(vnp[v, :16].copy()).view(4, 4), t(vnp[v, 16:32].copy()).view(4, 4), deg,
+                                            t(vnp[v, 32:35].copy()), False, False)
+        out = {}
+        try:
+            for mode in (0, 2):
+                R.set_tile_culling(mode)
+                leaves = {k: x.clone().requires_grad_(True) for k, x in cloud.items()}
+                fs = R.forward_with_state(rs, leaves["means3D"].detach(), leaves["opacities"].detach(), shs=leaves["shs"].detach(),
+                                          scales=leaves["scales"].detach(), rotations=leaves["rotations"].detach())
+                m2d = torch.zeros(N, 3, device=dev, requires_grad=True)
+                color, radii, depth, alpha = R.GaussianRasterizer(rs)(
+                    means3D=leaves["means3D"], means2D=m2d, shs=leaves["shs"], opacities=leaves["opacities"],
+                    scales=leaves["scales"], rotations=leaves["rotations"])
+                up = _upstream(H, W, 5)
+                (color * up[0].to(dev)).sum().add((depth * up[1].to(dev)).sum()).add((alpha * up[2].to(dev)).sum()).backward()
+                out[mode] = (fs, color.detach(), depth.detach(), alpha.detach(), radii,
+                             [leaves[k].grad.clone() for k in NAMES] + [m2d.grad.clone()])
+        finally:
+            R.set_tile_culling(1)
+        f0, f2 = out[0][0], out[2][0]
+        for i in (1, 2, 3, 4):
+            assert torch.equal(out[0][i], out[2][i])
+        assert torch.equal(f0["color"], f2["color"]) and torch.equal(f0["final_T"], f2["final_T"])
+        assert f2["num_rendered"] <= f0["num_rendered"]
+        if kind != "big":
+            assert f2["num_rendered"] < f0["num_rendered"]
+        # per-tile sub-list check: walk both lists with two pointers
+        r0, r2 = f0["ranges"].cpu().numpy().astype(np.int64), f2["ranges"].cpu().numpy().astype(np.int64)
+        l0, l2 = f0["point_list"].cpu().numpy(), f2["point_list"].cpu().numpy()
+        for tile in range(r0.shape[0]):
+            a = l0[r0[tile, 0]:r0[tile, 1]]; b = l2[r2[tile, 0]:r2[tile, 1]]
+            if b.size == 0:
+                continue
+            pos = np.flatnonzero(np.isin(a, b))
+            assert pos.size == b.size and np.array_equal(a[pos], b), f"tile {tile}"
+        for ga, gb, nm in zip(out[0][5], out[2][5], NAMES + ("means2D",)):
+            # same terms, different atomic summation order (rotation/scale grads are sums of cancelling terms)
+            assert float((ga - gb).norm()) <= GRAD_RTOL * float(ga.norm()) + 1e-12, nm
 
 
 # ---------------- full-size properties (BASELINE config 1: 1M Gaussians, 1080p) -----------------------
