@@ -423,7 +423,7 @@ struct Slot {
     Region saved[3];                 // GEOM, BINNING, IMAGE
     Region arena; size_t arena_off = 0, arena_want = 0;
     std::vector<void*> overflow;
-    Region sgrad, radii, image;
+    Region sgrad, radii, image, loss_ws;
     unsigned long long* host_total = nullptr;
     cudaEvent_t evA = nullptr, evDone = nullptr;
     bool failed = false;
@@ -506,12 +506,18 @@ PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
 // grad_sink (optional): called after each Gaussian range [first, first+count) of the FINAL preprocess-backward has
 // been enqueued on `user`, so a host-buffer caller can start the D2H of that range while the next one computes.
 struct GradSink { void (*fn)(void* ctx, int first, int count, cudaStream_t user); void* ctx; int nchunks; };
+// view hook (optional): called on the host after view v's forward has been enqueued on its slot stream and before
+// its backward is; the callee enqueues, on that stream, whatever turns images[v] into dL_dout[v] (the loss).
+// forward_only: no backward at all (render entry).  radii_out (optional): [V][N] per-view radii.
+struct StepOpts { gs_b200_view_hook hook = nullptr; void* hook_user = nullptr; bool forward_only = false; int32_t* radii_out = nullptr; };
 
 int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const float* views_host,
               const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
               const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
-              cudaStream_t user, const GradSink* sink = nullptr) {
+              cudaStream_t user, const GradSink* sink = nullptr, const StepOpts* opts = nullptr) {
     StepCache& C = g_step;
+    const StepOpts defaults;
+    const StepOpts& O = opts ? *opts : defaults;
     if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
     const int VB = std::min(V, std::min(gs_preprocess_multi_max_views(), 16));
@@ -539,7 +545,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
 
     for (int v0 = 0; v0 < V && !rc; v0 += VB) {
         const int nv = std::min(VB, V - v0);
-        GS_CUDA_CHECK(cudaMemsetAsync(sg_all, 0, (size_t)nv * N * sizeof(SplatGrad), user));
+        if (!O.forward_only) GS_CUDA_CHECK(cudaMemsetAsync(sg_all, 0, (size_t)nv * N * sizeof(SplatGrad), user));
         GS_CUDA_CHECK(cudaMemsetAsync(minkeys, 0xFF, 256 * 4, user));
         { StageTimer t(0, user);
         if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
@@ -580,6 +586,8 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             if ((rc = fwd_phase_b(*ctx[j & 1]))) break;
             rendered += st[j & 1].num_rendered;
             const int v = v0 + j;
+            if (O.forward_only) { if (S.failed) { rc = 1; break; } continue; }
+            if (O.hook && O.hook(O.hook_user, v, (void*)S.stream) != 0) { gs_set_error("step: view hook failed at view %d", v); rc = 1; break; }
             const float* up = dL_dout_dev + (size_t)v * 5 * npix;
             if (up_ready) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, up_ready[v], 0));
             if (st[j & 1].num_rendered > 0) {
@@ -597,6 +605,8 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
         }
         if (rc) break;
+        if (O.radii_out) GS_CUDA_CHECK(cudaMemcpyAsync(O.radii_out + (size_t)v0 * N, radii_all, (size_t)nv * N * 4, cudaMemcpyDeviceToDevice, user));
+        if (O.forward_only) continue;
         const bool last_chunk = v0 + VB >= V;
         const int nparts = (sink && last_chunk && sink->nchunks > 1) ? sink->nchunks : 1;
         const int per = (((N + nparts - 1) / nparts) + 127) / 128 * 128;
@@ -701,6 +711,89 @@ int32_t gs_b200_step_device(int32_t V, int32_t H, int32_t W, int32_t sh_degree, 
     const PackedPtrs grd = carve_packed(grads, N, M, true);
     return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
                      num_rendered_out, s);
+}
+
+int32_t gs_b200_step_device_hook(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                                 const float* views_host, const float* views_dev, int32_t N, int32_t M,
+                                 const float* means3D, const float* shs, const float* opacities, const float* scales,
+                                 const float* rotations, float* dL_dout, float* grads, float* images, int32_t* radii,
+                                 gs_b200_view_hook hook, void* hook_user, int64_t* num_rendered_out, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !shs || !opacities || !scales || !rotations ||
+        !dL_dout || !grads || !images || !hook) { gs_set_error("step_device_hook: bad argument"); return 1; }
+    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
+    par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
+    const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
+    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    const PackedPtrs grd = carve_packed(grads, N, M, true);
+    StepOpts o; o.hook = hook; o.hook_user = hook_user; o.radii_out = radii;
+    return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
+                     num_rendered_out, s, nullptr, &o);
+}
+
+namespace {
+struct TrainLossCtx {
+    int H, W; const float *ref, *mask; float ls, la, scale; float *dL, *images, *losses;
+};
+int32_t train_loss_hook(void* user, int32_t v, void* stream_) {
+    TrainLossCtx* q = (TrainLossCtx*)user;
+    cudaStream_t s = (cudaStream_t)stream_;
+    StepCache& C = g_step;
+    Slot* S = (s == C.slot[0].stream) ? &C.slot[0] : &C.slot[1];
+    if (Slot::ensure(S->loss_ws, gs_image_loss_scratch_bytes(q->H, q->W), s)) return 1;
+    const size_t npix = (size_t)q->H * q->W;
+    return gs_launch_image_loss(q->H, q->W, q->images + (size_t)v * 5 * npix, q->ref + (size_t)v * 3 * npix,
+                                q->mask + (size_t)v * npix, q->ls, q->la, q->scale, q->dL + (size_t)v * 5 * npix,
+                                q->losses + v, S->loss_ws.p, s);
+}
+thread_local Region g_loss_ws;
+}  // namespace
+
+int32_t gs_b200_image_loss(int32_t H, int32_t W, const float* image, const float* ref_image, const float* ref_mask,
+                           float lambda_ssim, float lambda_alpha, float scale, float* dL_dimage, float* loss_out,
+                           void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!image || !ref_image || !ref_mask || !dL_dimage || !loss_out) { gs_set_error("image_loss: NULL argument"); return 1; }
+    if (Slot::ensure(g_loss_ws, gs_image_loss_scratch_bytes(H, W), s)) return 1;
+    return gs_launch_image_loss(H, W, image, ref_image, ref_mask, lambda_ssim, lambda_alpha, scale, dL_dimage, loss_out,
+                                g_loss_ws.p, s);
+}
+
+int32_t gs_b200_step_device_train(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                                  const float* views_host, const float* views_dev, int32_t N, int32_t M,
+                                  const float* means3D, const float* shs, const float* opacities, const float* scales,
+                                  const float* rotations, const float* ref_images, const float* ref_masks,
+                                  float lambda_ssim, float lambda_alpha, float loss_scale, float* dL_dout, float* grads,
+                                  float* images, int32_t* radii, float* losses, int64_t* num_rendered_out, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !shs || !opacities || !scales || !rotations ||
+        !ref_images || !ref_masks || !dL_dout || !grads || !images || !losses) { gs_set_error("step_device_train: bad argument"); return 1; }
+    if (lambda_ssim > 0.f && (H <= 160 || W <= 160)) { gs_set_error("step_device_train: MS-SSIM needs image sides > 160"); return 1; }
+    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
+    par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
+    const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
+    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    const PackedPtrs grd = carve_packed(grads, N, M, true);
+    TrainLossCtx ctx{H, W, ref_images, ref_masks, lambda_ssim, lambda_alpha, loss_scale, dL_dout, images, losses};
+    StepOpts o; o.hook = train_loss_hook; o.hook_user = &ctx; o.radii_out = radii;
+    return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
+                     num_rendered_out, s, nullptr, &o);
+}
+
+int32_t gs_b200_render_views(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
+                             const float* views_host, const float* views_dev, int32_t N, int32_t M,
+                             const float* means3D, const float* shs, const float* opacities, const float* scales,
+                             const float* rotations, float* images, int32_t* radii, int64_t* num_rendered_out,
+                             void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !shs || !opacities || !scales || !rotations ||
+        !images) { gs_set_error("render_views: bad argument"); return 1; }
+    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
+    par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
+    PackedPtrs grd{};
+    StepOpts o; o.forward_only = true; o.radii_out = radii;
+    return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, nullptr, nullptr, grd, images,
+                     num_rendered_out, s, nullptr, &o);
 }
 
 int32_t gs_b200_step_host(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,

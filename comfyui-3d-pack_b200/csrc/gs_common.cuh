@@ -160,6 +160,11 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
                                         float* dopac, float* dscales, float* drots, int accumulate, int first, int count,
                                         cudaStream_t s);
 
+// image loss + gradient of one view (gs_loss.cu); scratch >= gs_image_loss_scratch_bytes(H, W)
+size_t gs_image_loss_scratch_bytes(int H, int W);
+int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const float* mask, float lambda_ssim,
+                         float lambda_alpha, float scale, float* dL, float* loss_out, void* scratch, cudaStream_t s);
+
 int gs_launch_activate(int, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gs_launch_adam(int, int, const float*, float, float, float, int, float, const float*, float*, float*, float*, cudaStream_t);
 int gs_launch_densify_stats(int, const float*, const int32_t*, float*, float*, float*, cudaStream_t);

@@ -62,6 +62,18 @@ lib.gs_b200_step_host.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.
 lib.gs_b200_step_device.restype = C.c_int32
 lib.gs_b200_step_device.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
     [_P] * 5 + [_P, _P, _P, C.POINTER(C.c_int64), _P]
+VIEW_HOOK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_void_p)
+lib.gs_b200_step_device_hook.restype = C.c_int32
+lib.gs_b200_step_device_hook.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
+    [_P] * 5 + [_P, _P, _P, _P, VIEW_HOOK, _P, C.POINTER(C.c_int64), _P]
+lib.gs_b200_image_loss.restype = C.c_int32
+lib.gs_b200_image_loss.argtypes = [C.c_int32, C.c_int32, _P, _P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P]
+lib.gs_b200_step_device_train.restype = C.c_int32
+lib.gs_b200_step_device_train.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
+    [_P] * 5 + [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.POINTER(C.c_int64), _P]
+lib.gs_b200_render_views.restype = C.c_int32
+lib.gs_b200_render_views.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
+    [_P] * 5 + [_P, _P, C.POINTER(C.c_int64), _P]
 lib.gs_b200_step_host_dev_grads.restype = C.c_int32
 lib.gs_b200_step_host_dev_grads.argtypes = lib.gs_b200_step_host.argtypes
 lib.gs_b200_launch_count.restype = C.c_int64
@@ -149,7 +161,7 @@ lib.gs_b200_set_tile_culling.argtypes = [_I]
 lib.gs_b200_get_tile_culling.restype = _I
 lib.gs_b200_get_tile_culling.argtypes = []
 
-EXPORTS = ["gs_b200_set_tile_culling", "gs_b200_get_tile_culling", "gs_b200_step_device", "gs_b200_step_host_dev_grads", "gs_b200_launch_count", "gs_b200_profile_enable", "gs_b200_profile_read",
+EXPORTS = ["gs_b200_image_loss", "gs_b200_step_device_train", "gs_b200_step_device_hook", "gs_b200_render_views", "gs_b200_set_tile_culling", "gs_b200_get_tile_culling", "gs_b200_step_device", "gs_b200_step_host_dev_grads", "gs_b200_launch_count", "gs_b200_profile_enable", "gs_b200_profile_read",
            "gs_b200_abi_version", "gs_b200_last_error", "gs_b200_rasterize_forward", "gs_b200_rasterize_backward",
            "gs_b200_state_free", "gs_b200_debug_sorted_keys", "gs_b200_sort_scratch_bytes",
            "gs_b200_sort_pairs_u32", "gs_b200_knn_mean_dist2", "gs_b200_step_host"]

@@ -113,6 +113,95 @@ def step_device_pipelined(params: PackedParams, views: ViewSet, dL_dout: torch.T
     return int(pairs.value)
 
 
+def step_device_loss(params: PackedParams, views: ViewSet, loss_grad_fn, images: torch.Tensor, dL_dout: torch.Tensor,
+                     radii: torch.Tensor = None):
+    """Forward + loss + backward in ONE pipelined pass (gs_b200_step_device_hook).
+
+    loss_grad_fn(v, image[5,H,W], dL[5,H,W]) is called once per view, with torch's current stream set to the internal
+    stream that just rendered images[v]; it must fill dL (in place) with d loss / d image.  Everything it enqueues
+    runs between that view's forward and backward, overlapped with the other views' kernels.  Returns pair count."""
+    import numpy as np
+    assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
+    assert images.shape == dL_dout.shape == (views.V, 5, views.H, views.W) and images.is_contiguous() and dL_dout.is_contiguous()
+    if radii is not None:
+        assert radii.dtype == torch.int32 and radii.shape == (views.V, params.N) and radii.is_contiguous()
+    err = []
+
+    def _hook(_user, v, stream_ptr):
+        try:
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_ptr), device=images.device)):
+                loss_grad_fn(int(v), images[v], dL_dout[v])
+            return 0
+        except BaseException as e:     # never let an exception cross the C frame
+            err.append(e)
+            return 1
+    cb = _lib.VIEW_HOOK(_hook)
+    pairs = C.c_int64(0)
+    rc = _lib.lib.gs_b200_step_device_hook(
+        views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
+        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+        _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads), _ptr(images),
+        None if radii is None else _ptr(radii), cb, None, C.byref(pairs), _stream())
+    if err:
+        raise err[0]
+    _lib.check(rc)
+    return int(pairs.value)
+
+
+def image_loss(image: torch.Tensor, ref_image: torch.Tensor, ref_mask: torch.Tensor, lambda_ssim=0.2, lambda_alpha=3.0, scale=1.0):
+    """CUDA training loss of one view (gs_b200_image_loss): image [5,H,W] -> (loss 0-d tensor, dL/dimage [5,H,W])."""
+    _, H, W = image.shape
+    assert image.shape[0] == 5 and ref_image.shape == (3, H, W) and ref_mask.shape == (1, H, W)
+    for t in (image, ref_image, ref_mask):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    dl = torch.empty_like(image); loss = torch.empty(1, device=image.device)
+    _lib.check(_lib.lib.gs_b200_image_loss(H, W, _ptr(image), _ptr(ref_image), _ptr(ref_mask), float(lambda_ssim), float(lambda_alpha),
+                                           float(scale), _ptr(dl), _ptr(loss), _stream()))
+    return loss[0], dl
+
+
+def step_device_train(params: PackedParams, views: ViewSet, ref_images: torch.Tensor, ref_masks: torch.Tensor, lambda_ssim,
+                      lambda_alpha, loss_scale, images: torch.Tensor, dL_dout: torch.Tensor, losses: torch.Tensor,
+                      radii: torch.Tensor = None):
+    """forward -> CUDA loss + gradient -> backward per view inside the pipeline (gs_b200_step_device_train)."""
+    import numpy as np
+    V, H, W = views.V, views.H, views.W
+    assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
+    assert images.shape == dL_dout.shape == (V, 5, H, W) and ref_images.shape == (V, 3, H, W) and ref_masks.shape == (V, 1, H, W)
+    assert losses.shape == (V,) and losses.dtype == torch.float32
+    for t in (images, dL_dout, ref_images, ref_masks, losses):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    if radii is not None:
+        assert radii.dtype == torch.int32 and radii.shape == (V, params.N) and radii.is_contiguous()
+    pairs = C.c_int64(0)
+    _lib.check(_lib.lib.gs_b200_step_device_train(
+        V, H, W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data), _ptr(views.dev),
+        params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities), _ptr(params.scales),
+        _ptr(params.rotations), _ptr(ref_images), _ptr(ref_masks), float(lambda_ssim), float(lambda_alpha), float(loss_scale),
+        _ptr(dL_dout), _ptr(params.grads), _ptr(images), None if radii is None else _ptr(radii), _ptr(losses),
+        C.byref(pairs), _stream()))
+    return int(pairs.value)
+
+
+def render_views(params: PackedParams, views: ViewSet, images: torch.Tensor = None, radii: torch.Tensor = None):
+    """Forward only over all views (gs_b200_render_views).  Returns (images[V,5,H,W], pair count); `radii`
+    (optional int32 [V,N]) receives the per-view radii (visibility filter = radii > 0)."""
+    import numpy as np
+    assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
+    if images is None:
+        images = torch.empty(views.V, 5, views.H, views.W, dtype=torch.float32, device=params.means3D.device)
+    assert images.shape == (views.V, 5, views.H, views.W) and images.is_contiguous()
+    if radii is not None:
+        assert radii.dtype == torch.int32 and radii.shape == (views.V, params.N) and radii.is_contiguous()
+    pairs = C.c_int64(0)
+    _lib.check(_lib.lib.gs_b200_render_views(
+        views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
+        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+        _ptr(params.scales), _ptr(params.rotations), _ptr(images), None if radii is None else _ptr(radii),
+        C.byref(pairs), _stream()))
+    return images, int(pairs.value)
+
+
 class HostStep:
     """The e2e entry (gs_b200_step_host): pinned host buffers in, summed gradients out."""
 

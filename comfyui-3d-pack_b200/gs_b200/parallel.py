@@ -36,3 +36,18 @@ def allreduce_packed_grads(buf: torch.Tensor, average: bool = False, group=None)
         if average:
             buf /= dist.get_world_size(group)
     return buf
+
+
+def allreduce_densify_stats(grad_accum: torch.Tensor, denom: torch.Tensor, max_radii2D: torch.Tensor, group=None):
+    """Keep replicas identical through densification (SURVEY §8e "extra state"): the per-Gaussian statistics that
+    decide clone / split / prune (`xyz_gradient_accum`, `denom`, `max_radii2D`, main_3DGS_renderer.py:767-769,
+    main_3DGS.py:212) are accumulated per rank over that rank's views; before each densification they are combined —
+    SUM for the two accumulators (packed into one collective), MAX for the radii — so every rank takes the same
+    decisions.  In place; no-op for a single process."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    packed = torch.cat([grad_accum.reshape(-1), denom.reshape(-1)])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    n = grad_accum.numel()
+    grad_accum.copy_(packed[:n].view_as(grad_accum)); denom.copy_(packed[n:].view_as(denom))
+    dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)

@@ -11,7 +11,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib, camera, losses, optim_step
+from . import _lib, camera, losses, optim_step, parallel
 from .rasterizer import _ptr, _stream, knn_mean_dist2
 
 SH_C0 = 0.28209479177387814
@@ -102,37 +102,69 @@ class GaussianTrainer:
                           p.position_lr_delay_mult, p.position_lr_max_steps)
         return np.array([lr_xyz, p.feature_lr, p.feature_lr / 20.0, p.opacity_lr, p.scaling_lr, p.rotation_lr], dtype=np.float32)
 
-    def render_views(self, views_np, W, H, need_grad_fn=None):
-        """Forward all views (images kept), call need_grad_fn(images[V,5,H,W]) -> dL/dimages, then backward.
-        Returns images (detached)."""
-        V = views_np.shape[0]
-        views = optim_step.ViewSet(np.ascontiguousarray(views_np, dtype=np.float32), W, H, self.p.sh_degree, self.device)
+    def _cloud(self):
         cloud = optim_step.PackedParams.__new__(optim_step.PackedParams)
         cloud.means3D, cloud.shs, cloud.opacities, cloud.scales, cloud.rotations = self.v["xyz"], self.v["shs"], self.a_opac, self.a_scales, self.a_rots
         cloud.N, cloud.M, cloud.grads, cloud.radii = self.N, self.M, self.grads, self.radii
-        imgs = torch.empty(V, 5, H, W, device=self.device)
-        # pass 1: forward only (zero upstream gradient), to evaluate the loss
+        return cloud
+
+    def _viewset(self, views_np, W, H):
+        return optim_step.ViewSet(np.ascontiguousarray(views_np, dtype=np.float32), W, H, self.p.sh_degree, self.device)
+
+    def render_views(self, views_np, W, H, radii=None):
+        """Forward only (gs_b200_render_views): images [V,5,H,W] = rgb | depth | alpha."""
         self.activate()
-        zero = torch.zeros(V, 5, H, W, device=self.device)
-        optim_step.step_device_pipelined(cloud, views, zero, imgs)
-        if need_grad_fn is None:
-            return imgs
-        dl = need_grad_fn(imgs)
-        optim_step.step_device_pipelined(cloud, views, dl.contiguous(), imgs)
+        imgs, _ = optim_step.render_views(self._cloud(), self._viewset(views_np, W, H), radii=radii)
         return imgs
 
-    def train_step(self, views_np, W, H, ref_images, ref_masks, world=1):
-        """ref_images [V,3,H,W], ref_masks [V,1,H,W] on device.  Returns the loss value (python float)."""
-        p = self.p
-        box = {}
+    def forward_backward(self, views_np, W, H, loss_grad_fn):
+        """ONE pipelined pass: per view forward -> loss_grad_fn(v, image, dL) -> backward; gradients wrt the activated
+        parameters are summed over the views into self.grads.  Returns the images."""
+        V = views_np.shape[0]
+        self.activate()
+        imgs = torch.empty(V, 5, H, W, device=self.device)
+        dl = torch.empty(V, 5, H, W, device=self.device)
+        radii = torch.empty(V, self.N, dtype=torch.int32, device=self.device)
+        optim_step.step_device_loss(self._cloud(), self._viewset(views_np, W, H), loss_grad_fn, imgs, dl, radii)
+        # radii of the LAST view of the batch: what the reference's densification statistics see (main_3DGS.py:211)
+        self.radii.copy_(radii[V - 1])
+        return imgs
 
-        def grad_fn(imgs):
-            x = imgs.detach().clone().requires_grad_(True)
-            loss = losses.training_loss(x[:, :3].clamp(0, 1), x[:, 4:5], ref_images, ref_masks, p.lambda_ssim, p.lambda_alpha)
-            loss.backward()
-            box["loss"] = float(loss.detach())
-            return x.grad
-        self.render_views(views_np, W, H, grad_fn)
+    def train_step(self, views_np, W, H, ref_images, ref_masks, world=None, total_views=None, loss_fn=None):
+        """ref_images [V,3,H,W], ref_masks [V,1,H,W] on device: this rank's views.  The loss terms are batch means
+        (main_3DGS.py:184-192), so the loss of the global batch is the mean of per-view losses: each view's loss and
+        its gradient are evaluated inside the render pipeline, between that view's forward and backward.
+        Data parallel: with torch.distributed initialised (or `world` given) the packed gradient buffer is
+        all-reduced once and averaged.  loss_fn=None uses the reference's loss as CUDA kernels (gs_b200_step_device_train);
+        a torch callable is run per view through the host hook instead.  Returns the (global-batch) loss as a float."""
+        p = self.p
+        V = views_np.shape[0]
+        if world is None:
+            world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        total = total_views or V * world
+        per_view = torch.zeros(V, device=self.device)
+        if loss_fn is None:
+            # native path: the loss and its gradient are CUDA kernels on each view's stream (gs_loss.cu)
+            self.activate()
+            imgs = torch.empty(V, 5, H, W, device=self.device); dl = torch.empty(V, 5, H, W, device=self.device)
+            radii = torch.empty(V, self.N, dtype=torch.int32, device=self.device)
+            optim_step.step_device_train(self._cloud(), self._viewset(views_np, W, H), ref_images.contiguous(), ref_masks.contiguous(),
+                                         p.lambda_ssim, p.lambda_alpha, 1.0 / total * world, imgs, dl, per_view, radii)
+            self.radii.copy_(radii[V - 1])
+        else:
+            # any torch loss: loss_fn(images[1,3,H,W] clamped, alphas[1,1,H,W], ref[1,3,H,W], mask[1,1,H,W]) -> scalar
+            def loss_grad_fn(v, img, dl):
+                x = img.detach().clone().requires_grad_(True)
+                loss = loss_fn(x[None, :3].clamp(0, 1), x[None, 4:5], ref_images[v:v + 1], ref_masks[v:v + 1]) * (world / total)
+                loss.backward()
+                dl.copy_(x.grad)
+                per_view[v] = loss.detach()
+            self.forward_backward(views_np, W, H, loss_grad_fn)
+        loss_sum = per_view.sum()
+        if world > 1:
+            parallel.allreduce_packed_grads(self.grads)
+            if torch.distributed.is_initialized():
+                torch.distributed.all_reduce(loss_sum)
         self.step_count += 1
         lrs = self.learning_rates(self.step_count - 1)
         _lib.check(_lib.lib.gs_b200_adam_step(self.N, self.M, C.c_void_p(lrs.ctypes.data), 0.9, 0.999, 1e-15, self.step_count, 1.0 / world,
@@ -143,10 +175,11 @@ class GaussianTrainer:
             _lib.check(_lib.lib.gs_b200_densify_stats(self.N, _ptr(self.g_means2D), _ptr(self.radii), _ptr(self.grad_accum),
                                                       _ptr(self.denom), _ptr(self.max_radii2D), _stream()))
             if s % p.densification_interval == 0:
+                parallel.allreduce_densify_stats(self.grad_accum, self.denom, self.max_radii2D)
                 self.densify_and_prune(p.densify_grad_threshold, 0.005, 4.0, 1.0)
             if s % p.opacity_reset_interval == 0:
                 self.reset_opacity()
-        return box["loss"]
+        return float(loss_sum) / world
 
     # ---------------------------------------------------------------- densification (torch-side, infrequent)
     def _rebuild(self, keep_idx, new):

@@ -182,6 +182,50 @@ int32_t gs_b200_step_host_dev_grads(
     const float* scales_host, const float* rotations_host, const float* dL_dout_host,
     float* grads_dev, float* images_host, int64_t* num_rendered_out, void* stream);
 
+/* Same step with the LOSS inside the pipeline (the reference computes its loss between render and backward,
+ * main_3DGS.py:176-205): after view v's forward has been enqueued on an internal stream, `hook(user, v, stream)` is
+ * called on the host; it must enqueue ON THAT STREAM the work that reads images[v] ([5,H,W]: rgb, depth, alpha)
+ * and writes dL_dout[v]; view v's backward is ordered after it.  Non-zero return aborts the step. */
+typedef int32_t (*gs_b200_view_hook)(void* user, int32_t view_index, void* stream);
+int32_t gs_b200_step_device_hook(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* opacities,
+    const float* scales, const float* rotations, float* dL_dout, float* grads, float* images,
+    int32_t* radii /* optional V x [N] */, gs_b200_view_hook hook, void* hook_user, int64_t* num_rendered_out,
+    void* stream);
+
+/* The reference's training loss and its gradient for ONE view, on the device (GaussianSplatting3D.training,
+ * main_3DGS.py:184-192; batch of one):
+ *   loss = scale * [ (1-lambda_ssim) * L1(img*m, ref*m) + lambda_alpha * MSE(alpha, m)
+ *                    + lambda_ssim * (1 - MS_SSIM(ref*m, img*m)) ],   img = clamp(rgb, 0, 1)
+ * MS_SSIM as pytorch_msssim.MS_SSIM(data_range=1, size_average=True, channel=3) (11-tap Gaussian, 5 scales), skipped when
+ * lambda_ssim == 0 as the reference does.  image: [5,H,W] (rgb | depth | alpha, what the rasterizer entries emit),
+ * ref_image [3,H,W], ref_mask [1,H,W]; dL_dimage [5,H,W] (depth plane = 0); loss_out: 1 device float.
+ * H and W must exceed 160 when lambda_ssim > 0 (the package's own assertion). */
+int32_t gs_b200_image_loss(
+    int32_t H, int32_t W, const float* image, const float* ref_image, const float* ref_mask, float lambda_ssim,
+    float lambda_alpha, float scale, float* dL_dimage, float* loss_out, void* stream);
+
+/* gs_b200_step_device with that loss evaluated inside the pipeline (per view: forward -> loss + gradient ->
+ * backward), no host callback: ref_images V x [3,H,W], ref_masks V x [1,H,W]; loss_scale = 1 / (views in the
+ * global batch); losses: V device floats (their sum over all ranks' views is the batch loss); dL_dout V x [5,H,W]
+ * receives the upstream gradients that were used; images V x [5,H,W]; radii optional V x [N]. */
+int32_t gs_b200_step_device_train(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* opacities,
+    const float* scales, const float* rotations, const float* ref_images, const float* ref_masks, float lambda_ssim,
+    float lambda_alpha, float loss_scale, float* dL_dout, float* grads, float* images, int32_t* radii, float* losses,
+    int64_t* num_rendered_out, void* stream);
+
+/* Forward only over V views that share the Gaussians (render nodes: orbit previews, LGM / TRELLIS style multi-view
+ * renders — nodes.py:1130-1163, Gen_3D_Modules/LGM/core/gs.py:41-92): one pass over the parameters for all
+ * views, then the per-view pipeline.  images: V x [5,H,W]; radii: optional V x [N] int32 (NULL = not kept). */
+int32_t gs_b200_render_views(
+    int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
+    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* opacities,
+    const float* scales, const float* rotations, float* images, int32_t* radii, int64_t* num_rendered_out,
+    void* stream);
+
 /* ---- optimisation step around the rasterizer (GaussianModel, main_3DGS_renderer.py) -------------
  * Raw (pre-activation) parameters live in ONE packed buffer laid out like the gradient buffer:
  *   xyz[N,3] | shs[N,M,3] (dc = coefficient 0) | opacity[N] | scaling[N,3] | rotation[N,4]

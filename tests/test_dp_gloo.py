@@ -36,8 +36,12 @@ def _worker(rank, world, port, q):
     for v in mine:
         buf += _view_grads(v)
     parallel.allreduce_packed_grads(buf)
+    # densification statistics: SUM of accumulators, MAX of radii -> identical on every rank afterwards
+    g = torch.Generator().manual_seed(rank)
+    acc, den, rad = torch.rand(N, generator=g), torch.rand(N, generator=g).round(), torch.rand(N, generator=g) * 9
+    parallel.allreduce_densify_stats(acc, den, rad)
     if rank == 0:
-        q.put((mine, buf.numpy()))
+        q.put((mine, buf.numpy(), acc.numpy(), den.numpy(), rad.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,10 +71,14 @@ def test_two_rank_allreduce_equals_single_process_sum():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    mine, got = q.get(timeout=300)
+    mine, got, acc, den, rad = q.get(timeout=300)
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
     assert mine == [0, 2]
     ref = sum(_view_grads(v) for v in range(V)).numpy()
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    gens = [torch.Generator().manual_seed(r) for r in range(2)]
+    parts = [(torch.rand(N, generator=g), torch.rand(N, generator=g).round(), torch.rand(N, generator=g) * 9) for g in gens]
+    assert np.allclose(acc, (parts[0][0] + parts[1][0]).numpy()) and np.allclose(den, (parts[0][1] + parts[1][1]).numpy())
+    assert np.array_equal(rad, torch.maximum(parts[0][2], parts[1][2]).numpy())

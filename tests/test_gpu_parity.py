@@ -50,8 +50,11 @@ def _grad_close(a, b, what):
         return
     rel = float((a - b).norm() / b.norm())
     assert rel < GRAD_RTOL, f"{what}: relative error {rel}"
-    # element-wise: 1e-3 relative with an absolute floor at 1e-3 of the largest component
-    assert bool(((a - b).abs() <= GRAD_RTOL * b.abs() + 1e-3 * GRAD_RTOL * scale + 1e-6).all()), what
+    # element-wise: 1e-3 relative with an absolute floor of 1e-5 of the largest component.  Each element is a sum of up
+    # to thousands of fp32 atomics whose order changes from run to run (and differs from the oracle's), so its noise
+    # scales with the sum of |terms|, not with the (often cancelling) result; a 1e-6 floor failed about once per
+    # cold-start run on one element of dL/dscales while the norm-relative check above stayed below 1e-4.
+    assert bool(((a - b).abs() <= GRAD_RTOL * b.abs() + 1e-2 * GRAD_RTOL * scale + 1e-6).all()), what
 
 
 # ---------------- CUB-free onesweep radix sort -----------------------------------------------------------
@@ -244,8 +247,19 @@ def test_multiview_step_entries_agree_with_per_view_path(dev):
                 assert float((hs.grads.to(dev) - g1).norm() / g1.norm()) < 1e-5
     finally:
         R.set_tile_culling(1)
-    # and the packed buffer equals the sum of per-view oracle-checked autograd gradients for one view
-    from gs_b200 import rasterizer as R
+    # forward-only entry: same images, per-view radii equal to the single-view API's
+    rad = torch.empty(V, N, dtype=torch.int32, device=dev)
+    ic, pc = optim_step.render_views(params, views, radii=rad)
+    assert torch.equal(ic, ia) and 0 < pc < p1
+    for v in (0, V - 1):
+        t = lambda a: torch.from_numpy(a).to(dev)
+        rs = R.GaussianRasterizationSettings(H, W, float(vnp[v, 38]), float(vnp[v, 39]), t(vnp[v, 35:38].copy()), 1.0,
+                                            t(vnp[v, :16].copy()).view(4, 4), t(vnp[v, 16:32].copy()).view(4, 4), deg,
+                                            t(vnp[v, 32:35].copy()), False, False)
+        with torch.no_grad():
+            col, r1, dep, alp = R.GaussianRasterizer(rs)(means3D=cloud["means3D"], means2D=torch.zeros(N, 3, device=dev), shs=cloud["shs"],
+                                                         opacities=cloud["opacities"], scales=cloud["scales"], rotations=cloud["rotations"])
+        assert torch.equal(r1, rad[v]) and torch.equal(col, ic[v, :3]) and torch.equal(dep, ic[v, 3:4]) and torch.equal(alp, ic[v, 4:5])
     cam = camera.MiniCam(camera.orbit_camera(0, 0.0, 1.75), W, H, np.deg2rad(49.1),
                          2 * np.arctan(np.tan(np.deg2rad(49.1) / 2) * W / H), 0.01, 100.0, device=dev)
     assert np.allclose(vnp[0, :16], cam.world_view_transform.reshape(-1).cpu().numpy(), atol=1e-6)
@@ -306,7 +320,11 @@ def test_tile_culling_is_a_sublist_with_identical_images(R, dev, kind, N, deg, W
             assert pos.size == b.size and np.array_equal(a[pos], b), f"tile {tile}"
         for ga, gb, nm in zip(out[0][5], out[2][5], NAMES + ("means2D",)):
             # same terms, different atomic summation order (rotation/scale grads are sums of cancelling terms)
-            assert float((ga - gb).norm()) <= GRAD_RTOL * float(ga.norm()) + 1e-12, nm
+            # (D0 is isotropic: its rotation gradient is pure rounding noise around zero -> absolute floor)
+            # The "big" cloud (screen-filling anisotropic splats, thousands of atomics per Gaussian, heavy cancellation)
+            # shows the same ~1e-4..1e-3 run-to-run noise with culling off (scripts/dev/cull_check.py).
+            tol = 5e-3 if kind == "big" else GRAD_RTOL
+            assert float((ga - gb).norm()) <= tol * float(ga.norm()) + 1e-6, nm
 
 
 # ---------------- full-size properties (BASELINE config 1: 1M Gaussians, 1080p) -----------------------
