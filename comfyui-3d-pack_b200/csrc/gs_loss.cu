@@ -6,8 +6,8 @@
 // The torch restatement in gs_b200/losses.py is the checker (tests/test_gpu_trainer.py); this file exists because at
 // 1080p the ~200 small torch kernels of that graph cost more host time per view than the whole rasterizer step.
 //
-// Per view:  prep (mask, clamp, L1/MSE sums) -> per scale [row filter -> column filter + map sums -> pool] ->
-// coefficients (one thread) -> per scale, coarse to fine [row filter -> column filter + map derivatives ->
+// Per view:  prep (mask, clamp, L1/MSE sums) -> per scale [fused row+column filter + map sums -> pool] ->
+// coefficients (one thread) -> per scale, coarse to fine [fused row+column filter + map derivatives ->
 // transposed column filter -> transposed row filter + combine + pooled gradient of the coarser scale] -> final.
 // All planes are [3][H][W] fp32; everything is streaming / stencil work (HBM / L2 bound, < 1 GB per 1080p view).
 #include "gs_common.cuh"
@@ -62,57 +62,99 @@ prep_kernel(int npix, const float* __restrict__ img, const float* __restrict__ r
     if (threadIdx.x == 0) atomicAdd(&acc->mse_sum, mse);
 }
 
-// row filter: R[k][c][y][xo], k = {x, y, x^2, y^2, x y}, xo in [0, Wo)
-__global__ void __launch_bounds__(256)
-hpass_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ R) {
-    const int Wo = Ws - (WIN - 1);
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
-    if (xo >= Wo) return;
-    const float* xr = X + ((size_t)c * Hs + y) * Ws + xo;
-    const float* yr = Y + ((size_t)c * Hs + y) * Ws + xo;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
-#pragma unroll
-    for (int k = 0; k < WIN; k++) {
-        const float w = c_win[k], xv = xr[k], yv = yr[k];
-        a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1); a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
-    }
-    const size_t plane = (size_t)3 * Hs * Wo, o = ((size_t)c * Hs + y) * Wo + xo;
-    R[o] = a0; R[plane + o] = a1; R[2 * plane + o] = a2; R[3 * plane + o] = a3; R[4 * plane + o] = a4;
-}
-
+// Gaussian-window statistics of one 32x8 tile of window positions, fused row + column filter through shared memory:
+// the (32+10)x(8+10) input tile of X and Y is staged once, the row filter writes its five quantities
+// {x, y, x^2, y^2, xy} for 18 rows into shared memory, the column filter reads them back.  (The unfused version
+// round-tripped those five planes through HBM: 250 MB per 1080p scale-0 pass, twice per view.)
+constexpr int ST_W = 32, ST_H = 8, ST_IW = ST_W + WIN - 1, ST_IH = ST_H + WIN - 1;
 struct Stats { float mx, my, ex2, ey2, exy; };
-__device__ __forceinline__ Stats vfilter(const float* __restrict__ R, int Hs, int Wo, int c, int yo, int xo) {
-    const size_t plane = (size_t)3 * Hs * Wo;
-    const float* p = R + ((size_t)c * Hs + yo) * Wo + xo;
+
+__device__ __forceinline__ Stats tile_stats(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y,
+                                            float (*s_xy)[ST_IH][ST_IW], float (*s_r)[ST_IH][ST_W], bool& valid, int& xo, int& yo) {
+    const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
+    const int c = blockIdx.z, x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
+    const int tid = threadIdx.x;
+    const float* xc = X + (size_t)c * Hs * Ws;
+    const float* yc = Y + (size_t)c * Hs * Ws;
+    for (int i = tid; i < ST_IH * ST_IW; i += ST_W * ST_H) {
+        const int r = i / ST_IW, q = i - r * ST_IW;
+        const int gy = y0 + r, gx = x0 + q;
+        const bool in = gy < Hs && gx < Ws;
+        s_xy[0][r][q] = in ? xc[(size_t)gy * Ws + gx] : 0.f;
+        s_xy[1][r][q] = in ? yc[(size_t)gy * Ws + gx] : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < ST_IH * ST_W; i += ST_W * ST_H) {
+        const int r = i / ST_W, q = i - r * ST_W;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; k++) {
+            const float w = c_win[k], xv = s_xy[0][r][q + k], yv = s_xy[1][r][q + k];
+            a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1); a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
+        }
+        s_r[0][r][q] = a0; s_r[1][r][q] = a1; s_r[2][r][q] = a2; s_r[3][r][q] = a3; s_r[4][r][q] = a4;
+    }
+    __syncthreads();
+    const int lx = tid & (ST_W - 1), ly = tid / ST_W;
+    xo = x0 + lx; yo = y0 + ly;
+    valid = xo < Wo && yo < Ho;
     Stats s{0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < WIN; k++) {
         const float w = c_win[k];
-        const size_t o = (size_t)k * Wo;
-        s.mx = fmaf(w, p[o], s.mx); s.my = fmaf(w, p[plane + o], s.my); s.ex2 = fmaf(w, p[2 * plane + o], s.ex2);
-        s.ey2 = fmaf(w, p[3 * plane + o], s.ey2); s.exy = fmaf(w, p[4 * plane + o], s.exy);
+        s.mx = fmaf(w, s_r[0][ly + k][lx], s.mx); s.my = fmaf(w, s_r[1][ly + k][lx], s.my); s.ex2 = fmaf(w, s_r[2][ly + k][lx], s.ex2);
+        s.ey2 = fmaf(w, s_r[3][ly + k][lx], s.ey2); s.exy = fmaf(w, s_r[4][ly + k][lx], s.exy);
     }
     return s;
 }
 
-// column filter + SSIM / CS maps, summed per channel
-__global__ void __launch_bounds__(256)
-vpass_sums_kernel(int Hs, int Ws, const float* __restrict__ R, LossAcc* __restrict__ acc, int level) {
+// SSIM / CS maps summed per channel
+__global__ void __launch_bounds__(ST_W * ST_H)
+stats_sums_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, LossAcc* __restrict__ acc, int level) {
+    __shared__ float s_xy[2][ST_IH][ST_IW];
+    __shared__ float s_r[5][ST_IH][ST_W];
     __shared__ float s_red[8];
-    const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y, c = blockIdx.z;
+    bool valid; int xo, yo;
+    const Stats s = tile_stats(Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
     float ssim = 0.f, cs = 0.f;
-    if (xo < Wo && yo < Ho) {
-        const Stats s = vfilter(R, Hs, Wo, c, yo, xo);
+    if (valid) {
         const float mxx = s.mx * s.mx, myy = s.my * s.my, mxy = s.mx * s.my;
         const float sx = s.ex2 - mxx, sy = s.ey2 - myy, sxy = s.exy - mxy;
         cs = (2.f * sxy + SSIM_C2) / (sx + sy + SSIM_C2);
         ssim = ((2.f * mxy + SSIM_C1) / (mxx + myy + SSIM_C1)) * cs;
     }
+    const int c = blockIdx.z;
     ssim = block_sum(ssim, s_red);
     if (threadIdx.x == 0) atomicAdd(&acc->sums[level][c][0], ssim);
     cs = block_sum(cs, s_red);
     if (threadIdx.x == 0) atomicAdd(&acc->sums[level][c][1], cs);
+}
+
+// derivatives of (b*ssim + a*cs) wrt (mu_y, E[y^2], E[xy]) -> D[3][c][yo][xo]
+__global__ void __launch_bounds__(ST_W * ST_H)
+stats_maps_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, const LossAcc* __restrict__ acc, int level,
+                  float* __restrict__ D) {
+    __shared__ float s_xy[2][ST_IH][ST_IW];
+    __shared__ float s_r[5][ST_IH][ST_W];
+    bool valid; int xo, yo;
+    const Stats s = tile_stats(Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
+    if (!valid) return;
+    const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1), c = blockIdx.z;
+    const float b = acc->coef[level][c][0], a = acc->coef[level][c][1];
+    const float mxx = s.mx * s.mx, myy = s.my * s.my, mxy = s.mx * s.my;
+    const float sx = s.ex2 - mxx, sy = s.ey2 - myy, sxy = s.exy - mxy;
+    const float Dcs = sx + sy + SSIM_C2, inv_Dcs = 1.f / Dcs;
+    const float cs = (2.f * sxy + SSIM_C2) * inv_Dcs;
+    const float Dl = mxx + myy + SSIM_C1, inv_Dl = 1.f / Dl;
+    const float l = (2.f * mxy + SSIM_C1) * inv_Dl;
+    const float dcs_dexy = 2.f * inv_Dcs, dcs_dey2 = -cs * inv_Dcs;
+    const float dcs_dmy = (-2.f * s.mx + 2.f * s.my * cs) * inv_Dcs;
+    const float dl_dmy = (2.f * s.mx - 2.f * s.my * l) * inv_Dl;
+    const float w_cs = a + b * l;                 // d(b*l*cs + a*cs)/d cs
+    const size_t plane = (size_t)3 * Ho * Wo, o = ((size_t)c * Ho + yo) * Wo + xo;
+    D[o] = w_cs * dcs_dmy + b * cs * dl_dmy;
+    D[plane + o] = w_cs * dcs_dey2;
+    D[2 * plane + o] = w_cs * dcs_dexy;
 }
 
 // 2x2 average pooling, padding (Hs%2, Ws%2), zeros counted (count_include_pad)
@@ -167,30 +209,6 @@ __global__ void coef_kernel(int H, int W, float lambda_ssim, float lambda_alpha,
         loss += lambda_ssim * (1.f - ms * (1.f / 3.f));
     }
     *loss_out = scale * loss;
-}
-
-// column filter + derivatives of (b*ssim + a*cs) wrt (mu_y, E[y^2], E[xy]) -> D[3][c][yo][xo]
-__global__ void __launch_bounds__(256)
-vpass_maps_kernel(int Hs, int Ws, const float* __restrict__ R, const LossAcc* __restrict__ acc, int level, float* __restrict__ D) {
-    const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y, c = blockIdx.z;
-    if (xo >= Wo) return;
-    const float b = acc->coef[level][c][0], a = acc->coef[level][c][1];
-    const Stats s = vfilter(R, Hs, Wo, c, yo, xo);
-    const float mxx = s.mx * s.mx, myy = s.my * s.my, mxy = s.mx * s.my;
-    const float sx = s.ex2 - mxx, sy = s.ey2 - myy, sxy = s.exy - mxy;
-    const float Dcs = sx + sy + SSIM_C2, inv_Dcs = 1.f / Dcs;
-    const float cs = (2.f * sxy + SSIM_C2) * inv_Dcs;
-    const float Dl = mxx + myy + SSIM_C1, inv_Dl = 1.f / Dl;
-    const float l = (2.f * mxy + SSIM_C1) * inv_Dl;
-    const float dcs_dexy = 2.f * inv_Dcs, dcs_dey2 = -cs * inv_Dcs;
-    const float dcs_dmy = (-2.f * s.mx + 2.f * s.my * cs) * inv_Dcs;
-    const float dl_dmy = (2.f * s.mx - 2.f * s.my * l) * inv_Dl;
-    const float w_cs = a + b * l;                 // d(b*l*cs + a*cs)/d cs
-    const size_t plane = (size_t)3 * Ho * Wo, o = ((size_t)c * Ho + yo) * Wo + xo;
-    D[o] = w_cs * dcs_dmy + b * cs * dl_dmy;
-    D[plane + o] = w_cs * dcs_dey2;
-    D[2 * plane + o] = w_cs * dcs_dexy;
 }
 
 // transposed column filter: E[k][c][y][xo] = sum_j w[j] D[k][c][y - j][xo]
@@ -310,9 +328,9 @@ int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const
     if (lambda_ssim > 0.f) {
         for (int l = 0; l < LEVELS; l++) {
             const int Hs = p.h[l], Ws = p.w[l], Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-            hpass_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, PX + p.off[l], PY + p.off[l], R);
-            vpass_sums_kernel<<<dim3((Wo + 255) / 256, Ho, 3), 256, 0, s>>>(Hs, Ws, R, acc, l);
-            launches += 2;
+            stats_sums_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(Hs, Ws, PX + p.off[l],
+                                                                                                       PY + p.off[l], acc, l);
+            launches += 1;
             if (l + 1 < LEVELS) {
                 pool_kernel<<<dim3((p.w[l + 1] + 255) / 256, p.h[l + 1], 3), 256, 0, s>>>(Hs, Ws, p.h[l + 1], p.w[l + 1], PX + p.off[l],
                                                                                          PY + p.off[l], PX + p.off[l + 1], PY + p.off[l + 1]);
@@ -326,14 +344,14 @@ int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const
     if (lambda_ssim > 0.f) {
         for (int l = LEVELS - 1; l >= 0; l--) {
             const int Hs = p.h[l], Ws = p.w[l], Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-            hpass_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, PX + p.off[l], PY + p.off[l], R);
-            vpass_maps_kernel<<<dim3((Wo + 255) / 256, Ho, 3), 256, 0, s>>>(Hs, Ws, R, acc, l, D);
-            vfull_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, D, R);          // E aliases R (R is dead here)
+            stats_maps_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(Hs, Ws, PX + p.off[l],
+                                                                                                       PY + p.off[l], acc, l, D);
+            vfull_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, D, R);
             const bool has_n = l + 1 < LEVELS;
             hfull_combine_kernel<<<dim3((Ws + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, R, PX + p.off[l], PY + p.off[l],
                                                                                has_n ? PG + p.off[l + 1] : nullptr, has_n ? p.h[l + 1] : 0,
                                                                                has_n ? p.w[l + 1] : 0, PG + p.off[l]);
-            launches += 4;
+            launches += 3;
         }
     }
     final_kernel<<<(npix + 255) / 256, 256, 0, s>>>(npix, img, mask, PX, PY, lambda_ssim > 0.f ? PG : nullptr, lambda_ssim,
