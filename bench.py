@@ -211,16 +211,25 @@ def run_b200(args):
 
     # ---- per-stage profile pass (events on the launching stream) -> roofline of the dominant kernel
     import ctypes as C
+    # The per-view C entries run the same kernels one view at a time.  Pair count of the package's own tile lists
+    # (culling off) = the K of SURVEY 8d's algorithmic-bytes formula; the timed stages run with culling on, like the step.
+    from gs_b200 import rasterizer as _R
+    mode0 = _R.get_tile_culling()
+    _R.set_tile_culling(0)
+    pairs_package = optim_step.step_device(params, views, dl)
+    _R.set_tile_culling(2 if mode0 >= 1 else 0)
     _lib.lib.gs_b200_profile_enable(1)
     prof_steps = 2
     for _ in range(prof_steps):
         optim_step.step_device(params, views, dl)
     torch.cuda.synchronize()
+    _R.set_tile_culling(mode0)
     ms = (C.c_float * _lib.NSTAGES)(); calls = (C.c_int32 * _lib.NSTAGES)()
     _lib.check(_lib.lib.gs_b200_profile_read(ms, calls))
     _lib.lib.gs_b200_profile_enable(0)
     stage_ms = {nm: (ms[i] / calls[i] if calls[i] else 0.0) for i, nm in enumerate(_lib.STAGE_NAMES)}
-    pairs_view = pairs / V
+    pairs_proc = pairs / V                  # (tile, splat) pairs the step actually processed (tile culling on)
+    pairs_view = pairs_package / V          # pairs of the package's tile lists: the algorithm's K*N
     npix = W * H
     c_in = 4 * (3 + 3 + 4 + 1 + 3 * M)
     # algorithmic bytes per launch (SURVEY §8d / DESIGN.md §5), with measured pairs per view
@@ -237,6 +246,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": stage_ms[dom],
+                "algorithmic_pairs": "package tile lists (K*N of SURVEY 8d); the kernels run on the culled lists",
                 "stage_ms_per_view": stage_ms,
                 "step_bytes_all_stages": sum(alg.values()) * V,
                 "step_hbm_frac": sum(alg.values()) * V / (ms_step * 1e-3) / 1e9 / peak}
@@ -296,7 +306,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"3DGS optimisation fwd+bwd: {N} Gaussians ({args.cloud} reference random-init), SH degree {deg}, "
                                f"{W}x{H}, {V}-view orbit per GPU (radius 1.75, fovy 49.1)",
-                   "views_per_gpu": V, "gaussians": N, "pairs_per_view": pairs_view,
+                   "views_per_gpu": V, "gaussians": N, "pairs_per_view": pairs_view, "pairs_per_view_after_tile_culling": pairs_proc,
                    "l2": "inputs larger than L2 (236 MB parameters + 8 x 41 MB upstream gradients per step vs 126 MB L2); no flush",
                    "parallelism": f"views sharded over {world} rank(s), Gaussians replicated" + (", one NCCL all-reduce of the packed gradient buffer per step" if world > 1 else "")},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
