@@ -16,7 +16,7 @@ namespace {
 
 constexpr int WIN = 11;
 constexpr int LEVELS = 5;
-__constant__ float c_win[WIN];
+struct Win { float w[WIN]; };        // 11-tap Gaussian, passed by value (no per-device constant state)
 __constant__ float c_msw[LEVELS] = {0.0448f, 0.2856f, 0.3001f, 0.2363f, 0.1333f};
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
 
@@ -69,7 +69,7 @@ prep_kernel(int npix, const float* __restrict__ img, const float* __restrict__ r
 constexpr int ST_W = 32, ST_H = 8, ST_IW = ST_W + WIN - 1, ST_IH = ST_H + WIN - 1;
 struct Stats { float mx, my, ex2, ey2, exy; };
 
-__device__ __forceinline__ Stats tile_stats(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y,
+__device__ __forceinline__ Stats tile_stats(const Win& win, int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y,
                                             float (*s_xy)[ST_IH][ST_IW], float (*s_r)[ST_IH][ST_W], bool& valid, int& xo, int& yo) {
     const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
     const int c = blockIdx.z, x0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
@@ -89,7 +89,7 @@ __device__ __forceinline__ Stats tile_stats(int Hs, int Ws, const float* __restr
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
         for (int k = 0; k < WIN; k++) {
-            const float w = c_win[k], xv = s_xy[0][r][q + k], yv = s_xy[1][r][q + k];
+            const float w = win.w[k], xv = s_xy[0][r][q + k], yv = s_xy[1][r][q + k];
             a0 = fmaf(w, xv, a0); a1 = fmaf(w, yv, a1); a2 = fmaf(w, xv * xv, a2); a3 = fmaf(w, yv * yv, a3); a4 = fmaf(w, xv * yv, a4);
         }
         s_r[0][r][q] = a0; s_r[1][r][q] = a1; s_r[2][r][q] = a2; s_r[3][r][q] = a3; s_r[4][r][q] = a4;
@@ -101,7 +101,7 @@ __device__ __forceinline__ Stats tile_stats(int Hs, int Ws, const float* __restr
     Stats s{0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < WIN; k++) {
-        const float w = c_win[k];
+        const float w = win.w[k];
         s.mx = fmaf(w, s_r[0][ly + k][lx], s.mx); s.my = fmaf(w, s_r[1][ly + k][lx], s.my); s.ex2 = fmaf(w, s_r[2][ly + k][lx], s.ex2);
         s.ey2 = fmaf(w, s_r[3][ly + k][lx], s.ey2); s.exy = fmaf(w, s_r[4][ly + k][lx], s.exy);
     }
@@ -110,12 +110,12 @@ __device__ __forceinline__ Stats tile_stats(int Hs, int Ws, const float* __restr
 
 // SSIM / CS maps summed per channel
 __global__ void __launch_bounds__(ST_W * ST_H)
-stats_sums_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, LossAcc* __restrict__ acc, int level) {
+stats_sums_kernel(Win win, int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, LossAcc* __restrict__ acc, int level) {
     __shared__ float s_xy[2][ST_IH][ST_IW];
     __shared__ float s_r[5][ST_IH][ST_W];
     __shared__ float s_red[8];
     bool valid; int xo, yo;
-    const Stats s = tile_stats(Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
+    const Stats s = tile_stats(win, Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
     float ssim = 0.f, cs = 0.f;
     if (valid) {
         const float mxx = s.mx * s.mx, myy = s.my * s.my, mxy = s.mx * s.my;
@@ -132,12 +132,12 @@ stats_sums_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __re
 
 // derivatives of (b*ssim + a*cs) wrt (mu_y, E[y^2], E[xy]) -> D[3][c][yo][xo]
 __global__ void __launch_bounds__(ST_W * ST_H)
-stats_maps_kernel(int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, const LossAcc* __restrict__ acc, int level,
+stats_maps_kernel(Win win, int Hs, int Ws, const float* __restrict__ X, const float* __restrict__ Y, const LossAcc* __restrict__ acc, int level,
                   float* __restrict__ D) {
     __shared__ float s_xy[2][ST_IH][ST_IW];
     __shared__ float s_r[5][ST_IH][ST_W];
     bool valid; int xo, yo;
-    const Stats s = tile_stats(Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
+    const Stats s = tile_stats(win, Hs, Ws, X, Y, s_xy, s_r, valid, xo, yo);
     if (!valid) return;
     const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1), c = blockIdx.z;
     const float b = acc->coef[level][c][0], a = acc->coef[level][c][1];
@@ -213,7 +213,7 @@ __global__ void coef_kernel(int H, int W, float lambda_ssim, float lambda_alpha,
 
 // transposed column filter: E[k][c][y][xo] = sum_j w[j] D[k][c][y - j][xo]
 __global__ void __launch_bounds__(256)
-vfull_kernel(int Hs, int Ws, const float* __restrict__ D, float* __restrict__ E) {
+vfull_kernel(Win win, int Hs, int Ws, const float* __restrict__ D, float* __restrict__ E) {
     const int Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
     const int xo = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
     if (xo >= Wo) return;
@@ -223,7 +223,7 @@ vfull_kernel(int Hs, int Ws, const float* __restrict__ D, float* __restrict__ E)
     for (int j = 0; j < WIN; j++) {
         const int yo = y - j;
         if (yo >= 0 && yo < Ho) {
-            const float w = c_win[j];
+            const float w = win.w[j];
             const size_t o = ((size_t)c * Ho + yo) * Wo + xo;
             e0 = fmaf(w, D[o], e0); e1 = fmaf(w, D[dplane + o], e1); e2 = fmaf(w, D[2 * dplane + o], e2);
         }
@@ -234,7 +234,7 @@ vfull_kernel(int Hs, int Ws, const float* __restrict__ D, float* __restrict__ E)
 
 // transposed row filter + combine with x, y + pooled gradient of the next coarser scale
 __global__ void __launch_bounds__(256)
-hfull_combine_kernel(int Hs, int Ws, const float* __restrict__ E, const float* __restrict__ X, const float* __restrict__ Y,
+hfull_combine_kernel(Win win, int Hs, int Ws, const float* __restrict__ E, const float* __restrict__ X, const float* __restrict__ Y,
                      const float* __restrict__ Gn /* coarser gradient or NULL */, int Hn, int Wn, float* __restrict__ G) {
     const int Wo = Ws - (WIN - 1);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, c = blockIdx.z;
@@ -246,7 +246,7 @@ hfull_combine_kernel(int Hs, int Ws, const float* __restrict__ E, const float* _
     for (int j = 0; j < WIN; j++) {
         const int xo = x - j;
         if (xo >= 0 && xo < Wo) {
-            const float w = c_win[j];
+            const float w = win.w[j];
             g0 = fmaf(w, e[xo], g0); g1 = fmaf(w, e[eplane + xo], g1); g2 = fmaf(w, e[2 * eplane + xo], g2);
         }
     }
@@ -276,16 +276,11 @@ final_kernel(int npix, const float* __restrict__ img, const float* __restrict__ 
     dL[(size_t)4 * npix + i] = scale * lambda_alpha * 2.f * (img[(size_t)4 * npix + i] - m) / (float)npix;
 }
 
-bool g_win_ready = false;
-int upload_window(cudaStream_t s) {
-    if (g_win_ready) return 0;
-    float w[WIN]; float sum = 0.f;
-    for (int i = 0; i < WIN; i++) { const float c = (float)(i - WIN / 2); w[i] = expf(-(c * c) / (2.f * 1.5f * 1.5f)); sum += w[i]; }
-    for (int i = 0; i < WIN; i++) w[i] /= sum;
-    GS_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_win, w, sizeof(w), 0, cudaMemcpyHostToDevice, s));
-    GS_CUDA_CHECK(cudaStreamSynchronize(s));
-    g_win_ready = true;
-    return 0;
+Win make_window() {
+    Win win; float sum = 0.f;
+    for (int i = 0; i < WIN; i++) { const float c = (float)(i - WIN / 2); win.w[i] = expf(-(c * c) / (2.f * 1.5f * 1.5f)); sum += win.w[i]; }
+    for (int i = 0; i < WIN; i++) win.w[i] /= sum;
+    return win;
 }
 
 struct Pyr { int h[LEVELS], w[LEVELS]; size_t off[LEVELS], total; };
@@ -314,7 +309,7 @@ int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const
     if (H <= 0 || W <= 0) { gs_set_error("image_loss: bad size"); return 1; }
     if (lambda_ssim > 0.f && (H <= (WIN - 1) * 16 || W <= (WIN - 1) * 16)) {
         gs_set_error("image_loss: image side must exceed 160 for the 4 downsamplings of MS-SSIM (%dx%d)", W, H); return 1; }
-    if (upload_window(s)) return 1;
+    const Win win = make_window();
     const Pyr p = make_pyr(H, W);
     const int npix = H * W;
     const size_t npix3 = (size_t)3 * npix;
@@ -328,7 +323,7 @@ int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const
     if (lambda_ssim > 0.f) {
         for (int l = 0; l < LEVELS; l++) {
             const int Hs = p.h[l], Ws = p.w[l], Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-            stats_sums_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(Hs, Ws, PX + p.off[l],
+            stats_sums_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(win, Hs, Ws, PX + p.off[l],
                                                                                                        PY + p.off[l], acc, l);
             launches += 1;
             if (l + 1 < LEVELS) {
@@ -344,11 +339,11 @@ int gs_launch_image_loss(int H, int W, const float* img, const float* ref, const
     if (lambda_ssim > 0.f) {
         for (int l = LEVELS - 1; l >= 0; l--) {
             const int Hs = p.h[l], Ws = p.w[l], Wo = Ws - (WIN - 1), Ho = Hs - (WIN - 1);
-            stats_maps_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(Hs, Ws, PX + p.off[l],
+            stats_maps_kernel<<<dim3((Wo + ST_W - 1) / ST_W, (Ho + ST_H - 1) / ST_H, 3), ST_W * ST_H, 0, s>>>(win, Hs, Ws, PX + p.off[l],
                                                                                                        PY + p.off[l], acc, l, D);
-            vfull_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, D, R);
+            vfull_kernel<<<dim3((Wo + 255) / 256, Hs, 3), 256, 0, s>>>(win, Hs, Ws, D, R);
             const bool has_n = l + 1 < LEVELS;
-            hfull_combine_kernel<<<dim3((Ws + 255) / 256, Hs, 3), 256, 0, s>>>(Hs, Ws, R, PX + p.off[l], PY + p.off[l],
+            hfull_combine_kernel<<<dim3((Ws + 255) / 256, Hs, 3), 256, 0, s>>>(win, Hs, Ws, R, PX + p.off[l], PY + p.off[l],
                                                                                has_n ? PG + p.off[l + 1] : nullptr, has_n ? p.h[l + 1] : 0,
                                                                                has_n ? p.w[l + 1] : 0, PG + p.off[l]);
             launches += 3;

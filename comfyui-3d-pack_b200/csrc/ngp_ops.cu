@@ -47,6 +47,8 @@ grid_encode_fwd_kernel(const float* __restrict__ x, long long N, const float2* _
     const uint32_t hsize = (uint32_t)(gm.off[l + 1] - gm.off[l]);
     const float2* table = emb + gm.off[l];
     float2 acc = make_float2(0.f, 0.f);
+    // (pairing the two x-neighbours into one 128-bit load, as the backward does for its reds, was measured neutral:
+    // 5.76 -> 5.92 ms on ray-ordered samples, 7.30 -> 6.38 ms on random ones; the gather is L1-wavefront bound)
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         const uint32_t bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
@@ -57,6 +59,11 @@ grid_encode_fwd_kernel(const float* __restrict__ x, long long N, const float2* _
     out[gid] = acc;
 }
 
+// V4: the two x-neighbours of a corner pair sit in ONE 16-byte-aligned float4 whenever their indices differ only in
+// bit 0 (always for even cell x in the hashed levels: (x+1)^h == (x^h)^1 and the table size is a power of two; for
+// even linear indices in the dense levels) -> one red.global.add.v4.f32 instead of two .v2 (L2 atomic units are
+// the bound of this kernel: profiles/r1_ngp_kernels.txt).
+template <bool V4>
 __global__ void __launch_bounds__(256)
 grid_encode_bwd_kernel(const float* __restrict__ x, long long N, GridMeta gm, const float2* __restrict__ g_out,
                        float2* __restrict__ d_emb) {
@@ -70,10 +77,20 @@ grid_encode_bwd_kernel(const float* __restrict__ x, long long N, GridMeta gm, co
     const uint32_t hsize = (uint32_t)(gm.off[l + 1] - gm.off[l]);
     float2* table = d_emb + gm.off[l];
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const uint32_t bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
-        const float w = (bx ? fr[0] : 1.f - fr[0]) * (by ? fr[1] : 1.f - fr[1]) * (bz ? fr[2] : 1.f - fr[2]);
-        atomicAdd(table + grid_index(pg[0] + bx, pg[1] + by, pg[2] + bz, gm.res[l], hsize), make_float2(w * g.x, w * g.y));   // red.global.add.v2.f32
+    for (int c = 0; c < 4; c++) {
+        const uint32_t by = c & 1, bz = (c >> 1) & 1;
+        const float wyz = (by ? fr[1] : 1.f - fr[1]) * (bz ? fr[2] : 1.f - fr[2]);
+        const float w0 = (1.f - fr[0]) * wyz, w1 = fr[0] * wyz;
+        const uint32_t i0 = grid_index(pg[0], pg[1] + by, pg[2] + bz, gm.res[l], hsize);
+        const uint32_t i1 = grid_index(pg[0] + 1, pg[1] + by, pg[2] + bz, gm.res[l], hsize);
+        if (V4 && (i0 ^ i1) == 1u) {
+            const bool lo0 = (i0 & 1u) == 0u;              // which of the two is the even (lower) entry
+            const float wa = lo0 ? w0 : w1, wb = lo0 ? w1 : w0;
+            atomicAdd(reinterpret_cast<float4*>(table + (i0 & ~1u)), make_float4(wa * g.x, wa * g.y, wb * g.x, wb * g.y));
+        } else {
+            atomicAdd(table + i0, make_float2(w0 * g.x, w0 * g.y));   // red.global.add.v2.f32
+            atomicAdd(table + i1, make_float2(w1 * g.x, w1 * g.y));
+        }
     }
 }
 
@@ -277,7 +294,9 @@ int ngp_grid_encode_bwd(const float* x, long long N, const int32_t* offsets_host
                         const float* g_out, float* d_emb, cudaStream_t s) {
     if (N <= 0) return 0;
     GridMeta gm; if (make_meta(gm, offsets_host, L, bound, pls, base)) return 1;
-    grid_encode_bwd_kernel<<<NGP_GRID(N * L), 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
+    static const bool v4 = []() { const char* e = getenv("NGP_B200_RED_V4"); return !(e && e[0] == '0'); }();
+    if (v4 && ((uintptr_t)d_emb & 15) == 0) grid_encode_bwd_kernel<true><<<NGP_GRID(N * L), 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
+    else grid_encode_bwd_kernel<false><<<NGP_GRID(N * L), 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
