@@ -265,6 +265,47 @@ def test_multiview_step_entries_agree_with_per_view_path(dev):
     assert np.allclose(vnp[0, :16], cam.world_view_transform.reshape(-1).cpu().numpy(), atol=1e-6)
 
 
+def test_multiview_entries_chunking_and_empty_views(dev):
+    """V = 18 > 16 views (two internal chunks), one view that sees nothing (all Gaussians behind the camera): the
+    pipelined, hook, train and render entries agree with the per-view C entries."""
+    from gs_b200 import camera, optim_step, synthetic
+    N, V, W, H, deg = 3000, 18, 192, 176, 1
+    cloud = synthetic.make_cloud("D1", N, deg, seed=9, device=dev)
+    params = optim_step.PackedParams(cloud)
+    vnp = camera.orbit_views(V, W, H).copy()
+    vnp[5, 14] = -50.0                       # view 5: world->view z translation far negative => every z_view <= 0.2
+    views = optim_step.ViewSet(vnp, W, H, deg, dev)
+    dl = (torch.rand(V, 5, H, W, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(dev)
+    ia = torch.empty(V, 5, H, W, device=dev); ib = torch.empty_like(ia); ic = torch.empty_like(ia)
+    optim_step.step_device(params, views, dl, ia); g1 = params.grads.clone()
+    assert float(ia[5, 4].abs().max()) == 0.0                          # nothing rendered in the empty view
+    optim_step.step_device_pipelined(params, views, dl, ib)
+    assert torch.equal(ia, ib) and float((params.grads - g1).norm() / g1.norm()) < 1e-5
+    rad = torch.empty(V, N, dtype=torch.int32, device=dev)
+    optim_step.render_views(params, views, ic, rad)
+    assert torch.equal(ia, ic) and int((rad[5] > 0).sum()) == 0 and int((rad[17] > 0).sum()) > 0
+    seen = []
+    def fn(v, img, out):
+        seen.append(v); out.copy_(dl[v])
+    dlh = torch.empty_like(dl)
+    optim_step.step_device_loss(params, views, fn, ic, dlh)
+    assert seen == list(range(V)) and torch.equal(dlh, dl)
+    assert float((params.grads - g1).norm() / g1.norm()) < 1e-5
+    # train entry: compare its upstream gradients / loss with the single-view CUDA loss, its parameter gradients
+    # with a plain step fed those upstream gradients
+    ref = torch.rand(V, 3, H, W, generator=torch.Generator().manual_seed(4)).to(dev)
+    msk = (torch.rand(V, 1, H, W, generator=torch.Generator().manual_seed(5)) > 0.3).float().to(dev)
+    lv = torch.zeros(V, device=dev); dlt = torch.empty_like(dl)
+    optim_step.step_device_train(params, views, ref, msk, 0.2, 3.0, 1.0 / V, ic, dlt, lv)
+    gt = params.grads.clone()
+    for v in (0, 5, 17):
+        l1, d1 = optim_step.image_loss(ia[v].contiguous(), ref[v].contiguous(), msk[v].contiguous(), 0.2, 3.0, 1.0 / V)
+        assert abs(float(l1) - float(lv[v])) <= 1e-6 * max(1.0, abs(float(l1)))
+        assert float((d1 - dlt[v]).abs().max()) <= 1e-6 * float(d1.abs().max()) + 1e-12
+    optim_step.step_device_pipelined(params, views, dlt)
+    assert float((params.grads - gt).norm() / gt.norm()) < 1e-5
+
+
 # ---------------- tile culling (optional tight tile lists) -----------------------------------------------
 @pytest.mark.parametrize("kind,N,deg,W,H", [("D1", 3000, 2, 200, 120), ("D0", 50000, 3, 640, 360), ("big", 400, 0, 320, 200)])
 def test_tile_culling_is_a_sublist_with_identical_images(R, dev, kind, N, deg, W, H):
