@@ -296,7 +296,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (contract): keeps multi-rank runs short
         sample = tuple(int(x) for x in args.cpu_sample.split(","))
         v, ms_cpu, cores, desc = cpu_sample_run(sample, deg, args.cloud, 1, 0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "ms_per_step": ms_cpu}
