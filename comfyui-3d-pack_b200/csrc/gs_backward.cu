@@ -287,7 +287,7 @@ preprocess_backward_kernel(ViewArgs va, int N, int M, const float* __restrict__ 
 
 // V views in one pass (SH + scale/rotation parameterisation only — what the optimisation step uses).
 // sg, radii: [V][N].
-__global__ void __launch_bounds__(PB_THREADS)
+__global__ void __launch_bounds__(PB_THREADS, 4)     // 128 registers, no spills: 4 CTAs / SM (was 168 -> 3)
 preprocess_backward_multi_kernel(const float* __restrict__ views, int V, int W, int H, int sh_degree,
                                  float scale_modifier, int N, int M, const float* __restrict__ means3D,
                                  const float* __restrict__ shs, const float* __restrict__ scales,
@@ -371,6 +371,8 @@ int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, in
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
         GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_backward_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_backward_multi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     int blocks = (count + PB_THREADS - 1) / PB_THREADS;

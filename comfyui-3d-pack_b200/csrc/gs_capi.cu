@@ -685,7 +685,7 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
             cudaMemcpyAsync(q->host + off, q->dev + off, (size_t)count * per[gI] * 4, cudaMemcpyDeviceToHost, C2.d2h_stream);
         }
     };
-    GS_CUDA_CHECK(cudaMemsetAsync(d_grad, 0, n_grad * 4, s));
+    // no memset of the gradient buffer: the first view chunk's preprocess-backward writes every element (accumulate = 0)
     if (step_core(V, H, W, sh_degree, scale_modifier, views_host, d_views, N, M, par, d_up, C.up_ready.data(), grd,
                   d_img, num_rendered_out, s, &sink)) return 1;
     if (grads_dev) GS_CUDA_CHECK(cudaMemcpyAsync(grads_dev, d_grad, n_grad * 4, cudaMemcpyDeviceToDevice, s));
@@ -707,7 +707,7 @@ int32_t gs_b200_step_device(int32_t V, int32_t H, int32_t W, int32_t sh_degree, 
     PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
     par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
     const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
-    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    (void)n_grad;   // grads need no memset: the first chunk's preprocess-backward writes every element
     const PackedPtrs grd = carve_packed(grads, N, M, true);
     return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
                      num_rendered_out, s);
@@ -724,7 +724,7 @@ int32_t gs_b200_step_device_hook(int32_t V, int32_t H, int32_t W, int32_t sh_deg
     PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
     par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
     const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
-    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    (void)n_grad;   // grads need no memset: the first chunk's preprocess-backward writes every element
     const PackedPtrs grd = carve_packed(grads, N, M, true);
     StepOpts o; o.hook = hook; o.hook_user = hook_user; o.radii_out = radii;
     return step_core(V, H, W, sh_degree, scale_modifier, views_host, views_dev, N, M, par, dL_dout, nullptr, grd, images,
@@ -772,7 +772,7 @@ int32_t gs_b200_step_device_train(int32_t V, int32_t H, int32_t W, int32_t sh_de
     PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
     par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
     const size_t n_grad = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4) + (size_t)N * 3;
-    GS_CUDA_CHECK(cudaMemsetAsync(grads, 0, n_grad * 4, s));
+    (void)n_grad;   // grads need no memset: the first chunk's preprocess-backward writes every element
     const PackedPtrs grd = carve_packed(grads, N, M, true);
     TrainLossCtx ctx{H, W, ref_images, ref_masks, lambda_ssim, lambda_alpha, loss_scale, dL_dout, images, losses};
     StepOpts o; o.hook = train_loss_hook; o.hook_user = &ctx; o.radii_out = radii;

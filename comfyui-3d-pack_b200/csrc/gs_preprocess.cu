@@ -109,28 +109,29 @@ __device__ __forceinline__ void tight_spans(float px, float py, const float4 cq,
     const float Ymax = sqrtf(k2 * inv_det), Xmax = sqrtf(2.0f * tau * C * inv_det);
     const float uyR = -(B * Xmax) / C;                      // y offset of the right-most point of the ellipse
     if (!(isfinite(Ymax) && isfinite(Xmax) && isfinite(uyR) && isfinite(px) && isfinite(py))) return;
-    uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    // rows beyond h are never visited (typical squares are 2-4 tiles high); entries are packed with 64-bit shifts so
+    // the loop needs no dynamically indexed array
+    unsigned long long lo64 = 0ull, hi64 = 0ull;
     uint32_t total = 0;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < h; r++) {
         uint32_t cnt = 0, start = 0;
-        if (r < h) {
-            const float a = (float)((y0 + r) * GS_TILE) - py, b = a + (float)(GS_TILE - 1);
-            const float lo = fmaxf(a, -Ymax), hi = fminf(b, Ymax);
-            if (lo <= hi) {
-                const float yr = fminf(fmaxf(uyR, lo), hi), yl = fminf(fmaxf(-uyR, lo), hi);
-                float xr = (-(B * yr) + sqrtf(fmaxf(k2 - det * yr * yr, 0.f))) * invA;
-                float xl = (-(B * yl) - sqrtf(fmaxf(k2 - det * yl * yl, 0.f))) * invA;
-                xr += 0.01f + 1e-4f * fabsf(xr);
-                xl -= 0.01f + 1e-4f * fabsf(xl);
-                const int ta = max(x0, (int)ceilf((px + xl - (float)(GS_TILE - 1)) * (1.0f / GS_TILE)));
-                const int tb = min(x1 - 1, (int)floorf((px + xr) * (1.0f / GS_TILE)));
-                if (tb >= ta) { cnt = (uint32_t)(tb - ta + 1); start = (uint32_t)(ta - x0); }
-            }
+        const float a = (float)((y0 + r) * GS_TILE) - py, b = a + (float)(GS_TILE - 1);
+        const float lo = fmaxf(a, -Ymax), hi = fminf(b, Ymax);
+        if (lo <= hi) {
+            const float yr = fminf(fmaxf(uyR, lo), hi), yl = fminf(fmaxf(-uyR, lo), hi);
+            float xr = (-(B * yr) + sqrtf(fmaxf(k2 - det * yr * yr, 0.f))) * invA;
+            float xl = (-(B * yl) - sqrtf(fmaxf(k2 - det * yl * yl, 0.f))) * invA;
+            xr += 0.01f + 1e-4f * fabsf(xr);
+            xl -= 0.01f + 1e-4f * fabsf(xl);
+            const int ta = max(x0, (int)ceilf((px + xl - (float)(GS_TILE - 1)) * (1.0f / GS_TILE)));
+            const int tb = min(x1 - 1, (int)floorf((px + xr) * (1.0f / GS_TILE)));
+            if (tb >= ta) { cnt = (uint32_t)(tb - ta + 1); start = (uint32_t)(ta - x0); }
         }
-        packed[r >> 1] |= (start | (cnt << 8)) << (16 * (r & 1));
+        const unsigned long long e = (unsigned long long)(start | (cnt << 8));
+        if (r < 4) lo64 |= e << (16 * r); else hi64 |= e << (16 * (r - 4));
         total += cnt;
     }
+    uint32_t packed[4] = {(uint32_t)lo64, (uint32_t)(lo64 >> 32), (uint32_t)hi64, (uint32_t)(hi64 >> 32)};
     count = total;
     spans = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
