@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -470,6 +471,7 @@ struct StepCache {
     cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr;
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
+    bool busy = false;                           // a view hook must not re-enter the step entries on this thread
     Region ws_recs, ws_sg, ws_u32, ws_spans;               // per-chunk [VB][N] arrays of the multi-view step
     int ensure_init() {
         if (init) return 0;
@@ -516,6 +518,8 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
               const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
               cudaStream_t user, const GradSink* sink = nullptr, const StepOpts* opts = nullptr) {
     StepCache& C = g_step;
+    if (C.busy) { gs_set_error("step: re-entrant call from a view hook (the per-thread pipeline state is in use)"); return 1; }
+    struct BusyGuard { bool& b; explicit BusyGuard(bool& x) : b(x) { b = true; } ~BusyGuard() { b = false; } } busy_guard(C.busy);
     const StepOpts defaults;
     const StepOpts& O = opts ? *opts : defaults;
     if (C.ensure_init()) return 1;
@@ -539,7 +543,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
 
     gs_b200_state st[2];
     gs_b200_view view[2];
-    FwdCtx* ctx[2] = {nullptr, nullptr};
+    std::unique_ptr<FwdCtx> ctx[2];                 // released on every exit path
     int64_t rendered = 0;
     int rc = 0;
 
@@ -567,8 +571,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             vw.bg = vd + 35; vw.scale_modifier = scale_modifier; vw.viewmatrix = vd; vw.projmatrix = vd + 16;
             vw.sh_degree = sh_degree; vw.campos = vd + 32; vw.prefiltered = 0; vw.debug = 0;
             float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
-            delete ctx[j & 1];
-            ctx[j & 1] = new FwdCtx(slot_alloc_cb, &S, S.stream);
+            ctx[j & 1].reset(new FwdCtx(slot_alloc_cb, &S, S.stream));
             const size_t o = (size_t)j * N;
             PreView pre{recs_all + o, tiles_all + o, dkeys_all + o, ids_all + o, minkeys + 2 * j,
                         spans_all ? spans_all + o : nullptr};
@@ -598,7 +601,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             }
             if (S.failed) { rc = 1; break; }
         }
-        for (int i = 0; i < 2; i++) { delete ctx[i]; ctx[i] = nullptr; }
+        for (int i = 0; i < 2; i++) ctx[i].reset();
         // join: the caller's stream continues after both slot streams
         for (int i = 0; i < 2; i++) {
             cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);

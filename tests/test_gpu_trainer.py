@@ -170,6 +170,11 @@ def test_pipelined_loss_step_equals_two_pass_step(dev):
         raise KeyError("boom")
     with pytest.raises(KeyError):
         tr.forward_backward(views, W, H, bad)
+    # a hook that re-enters the step entries is refused (per-thread pipeline state), not silently corrupted
+    def reenter(v, img, dl):
+        tr.render_views(views, W, H)
+    with pytest.raises(RuntimeError, match="re-entrant"):
+        tr.forward_backward(views, W, H, reenter)
     assert torch.equal(tr.render_views(views, W, H), imgs_a)
 
 
