@@ -221,10 +221,13 @@ class GaussianTrainer:
                   "rotation": self.v["rotation"][idx_s].repeat(Nn, 1), "shs": self.v["shs"][idx_s].repeat(Nn, 1, 1),
                   "opacity": self.v["opacity"][idx_s].repeat(Nn, 1)}
             new = {k: torch.cat([new[k], sp[k]], dim=0) for k in self.GROUPS}
-        # prune: split parents, low opacity, big on screen / in world (new points have max_radii2D = 0)
+        # prune: split parents, low opacity, big in world space.  The reference's screen-size rule
+        # (`max_radii2D > max_screen_size`, :774) never fires as written: densification_postfix has already reset
+        # max_radii2D to zeros for every point (:636-639) by the time prune() reads it — reproduced here (pinned by
+        # tests/test_golden_training.py against the reference's own class).
         n_old = self.N
         opac = torch.sigmoid(self.v["opacity"]).squeeze(1)
-        prune_old = split | (opac < min_opacity) | (self.max_radii2D > max_screen_size) | (scal > 0.1 * extent)
+        prune_old = split | (opac < min_opacity) | (scal > 0.1 * extent)
         n_op = torch.sigmoid(new["opacity"]).squeeze(1); n_sc = torch.exp(new["scaling"]).max(dim=1).values
         keep_new = ~((n_op < min_opacity) | (n_sc > 0.1 * extent))
         new = {k: v[keep_new] for k, v in new.items()}

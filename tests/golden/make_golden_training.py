@@ -1,0 +1,127 @@
+"""Generates tests/golden/ref_training.npz from the REFERENCE's own GaussianModel code, run on the CPU.
+
+    python tests/golden/make_golden_training.py        (build container only: needs /root/reference)
+
+Pins the host-side pieces either side of the rasterizer to the reference itself:
+  * get_expon_lr_func                        main_3DGS_renderer.py:21-43
+  * GaussianModel.densify_and_prune          :641-688, 752-781  (clone / split / prune incl. the Adam-state surgery
+                                             :543-639) on a seeded state, with torch.manual_seed fixed so that
+                                             torch.normal in densify_and_split draws the same numbers in the test
+  * GaussianModel.reset_opacity              :463-466
+  * GaussianModel.to_ply row layout + construct_list_of_gs_attributes   :475-484, mesh_processer/mesh_utils.py:333-345
+The class body is exec'd from the reference source with device="cuda" -> "cpu"; third-party names it only uses in
+other methods are stubbed.  Nothing from the reference is copied into the repo: only the numeric outputs are stored.
+"""
+import os, re, types
+import numpy as np
+import torch
+from torch import nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def load_reference_model():
+    src = open(os.path.join(REF, "MVs_Algorithms/GaussianSplatting/main_3DGS_renderer.py")).read()
+    a = src.index("def get_expon_lr_func(")
+    b = src.index("class GaussianSplattingRenderer")
+    body = src[a:b].replace('device="cuda"', 'device="cpu"').replace("device='cuda'", "device='cpu'")
+    mu = open(os.path.join(REF, "mesh_processer/mesh_utils.py")).read()
+    m = re.search(r"^def construct_list_of_gs_attributes\(.*?(?=^def )", mu, flags=re.S | re.M)
+    captured = {}
+
+    def write_gs_ply(xyz, normals, f_dc, f_rest, opacities, scale, rotation, names):
+        captured["rows"] = np.concatenate((xyz, normals, f_dc, f_rest, opacities, scale, rotation), axis=1)
+        captured["names"] = list(names)
+        return None
+
+    class _TT:                                   # torchtyping.TensorType["N", 4] in annotations
+        def __getitem__(self, k):
+            return torch.Tensor
+    ns = {"torch": torch, "nn": nn, "np": np, "TensorType": _TT(), "PointCloud": object, "Mesh": object,
+          "inverse_sigmoid": lambda x: torch.log(x / (1 - x)), "write_gs_ply": write_gs_ply,
+          "SH2RGB": None, "RGB2SH": None, "eval_sh": None, "read_gs_ply": None, "K_nearest_neighbors_func": None,
+          "math": __import__("math"), "F": torch.nn.functional}
+    exec(m.group(0), ns)
+    exec(compile(body, "ref_gaussian_model_cpu", "exec"), ns)
+    return ns, captured
+
+
+def main():
+    ns, captured = load_reference_model()
+    out = {}
+    # ---- lr schedule --------------------------------------------------------------------------------------------
+    f = ns["get_expon_lr_func"](lr_init=0.00016 * 10.0, lr_final=0.0000016 * 10.0, lr_delay_mult=0.01, max_steps=30000)
+    steps = np.array([0, 1, 10, 500, 2999, 15000, 30000, 40000], dtype=np.int64)
+    out["lr_steps"] = steps
+    out["lr_values"] = np.array([f(int(s)) for s in steps], dtype=np.float64)
+    f2 = ns["get_expon_lr_func"](lr_init=1e-2, lr_final=1e-4, lr_delay_steps=100, lr_delay_mult=0.1, max_steps=1000)
+    out["lr2_values"] = np.array([f2(int(s)) for s in (0, 50, 100, 1000)], dtype=np.float64)
+
+    # ---- densify_and_prune on a seeded state ---------------------------------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    N, deg = 600, 1
+    M = (deg + 1) ** 2
+    gm = ns["GaussianModel"](deg)
+    xyz = (torch.rand(N, 3, generator=g) - 0.5)
+    state = {
+        "xyz": xyz, "f_dc": torch.randn(N, 1, 3, generator=g), "f_rest": torch.randn(N, M - 1, 3, generator=g) * 0.1,
+        "scaling": torch.log(torch.rand(N, 3, generator=g) * 0.08 + 1e-3), "rotation": torch.randn(N, 4, generator=g),
+        "opacity": torch.randn(N, 1, generator=g) * 2.0}
+    state["scaling"][:15] = float(np.log(0.5))          # too big in world space -> pruned
+    state["opacity"][40:70] = -8.0                      # sigmoid < 0.005 -> pruned
+    gm._xyz = nn.Parameter(state["xyz"].clone()); gm.init_xyz = state["xyz"].clone()
+    gm._features_dc = nn.Parameter(state["f_dc"].clone()); gm._features_rest = nn.Parameter(state["f_rest"].clone())
+    gm._scaling = nn.Parameter(state["scaling"].clone()); gm._rotation = nn.Parameter(state["rotation"].clone())
+    gm._opacity = nn.Parameter(state["opacity"].clone())
+    gm.max_radii2D = torch.rand(N, generator=g) * 3.0    # some > max_screen_size = 1 (see the note in the test)
+    gm.spatial_lr_scale = 10.0
+    args = types.SimpleNamespace(percent_dense=0.01, position_lr_init=0.00016, position_lr_final=0.0000016,
+                                 position_lr_delay_mult=0.01, position_lr_max_steps=30000, feature_lr=0.0025,
+                                 opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001)
+    gm.training_setup(args)
+    # one optimizer step so that Adam moments exist and are non-trivial
+    for grp in gm.optimizer.param_groups:
+        p = grp["params"][0]
+        p.grad = torch.randn(p.shape, generator=g) * 1e-3
+    pre = {k: v.detach().clone() for k, v in (("xyz", gm._xyz), ("f_dc", gm._features_dc), ("f_rest", gm._features_rest),
+                                               ("scaling", gm._scaling), ("rotation", gm._rotation), ("opacity", gm._opacity))}
+    grads_in = {grp["name"]: grp["params"][0].grad.clone() for grp in gm.optimizer.param_groups}
+    gm.optimizer.step()
+    post_step = {grp["name"]: grp["params"][0].detach().clone() for grp in gm.optimizer.param_groups}
+    m1 = {grp["name"]: gm.optimizer.state[grp["params"][0]]["exp_avg"].clone() for grp in gm.optimizer.param_groups}
+    m2 = {grp["name"]: gm.optimizer.state[grp["params"][0]]["exp_avg_sq"].clone() for grp in gm.optimizer.param_groups}
+    gm.xyz_gradient_accum = torch.rand(N, 1, generator=g) * 4e-4
+    gm.denom = torch.ones(N, 1); gm.denom[100:130] = 0.0           # 0/0 -> NaN -> 0
+    for k in pre:                                  # state AFTER the optimizer step = what densification sees
+        out["pre_" + k] = post_step[{"xyz": "xyz", "f_dc": "f_dc", "f_rest": "f_rest", "scaling": "scaling", "rotation": "rotation", "opacity": "opacity"}[k]].numpy()
+    for k in grads_in:
+        out["m1_" + k] = m1[k].numpy(); out["m2_" + k] = m2[k].numpy()
+    out["grad_accum"] = gm.xyz_gradient_accum.numpy().copy(); out["denom"] = gm.denom.numpy().copy()
+    out["max_radii2D"] = gm.max_radii2D.numpy().copy()
+    out["adam_lrs"] = np.array([grp["lr"] for grp in gm.optimizer.param_groups], dtype=np.float64)
+    torch.manual_seed(1234)
+    gm.densify_and_prune(2e-4, min_opacity=0.005, extent=4, max_screen_size=1)
+    out["dens_seed"] = np.int64(1234)
+    for k, v in (("xyz", gm._xyz), ("f_dc", gm._features_dc), ("f_rest", gm._features_rest), ("scaling", gm._scaling),
+                 ("rotation", gm._rotation), ("opacity", gm._opacity)):
+        out["dens_" + k] = v.detach().numpy().copy()
+    for grp in gm.optimizer.param_groups:
+        st = gm.optimizer.state[grp["params"][0]]
+        out["dens_m1_" + grp["name"]] = st["exp_avg"].numpy().copy()
+        out["dens_m2_" + grp["name"]] = st["exp_avg_sq"].numpy().copy()
+    out["dens_max_radii2D"] = gm.max_radii2D.numpy().copy()
+    # ---- reset_opacity ----------------------------------------------------------------------------------------------
+    gm.reset_opacity()
+    out["reset_opacity"] = gm._opacity.detach().numpy().copy()
+    out["reset_m1_opacity"] = gm.optimizer.state[[grp for grp in gm.optimizer.param_groups if grp["name"] == "opacity"][0]["params"][0]]["exp_avg"].numpy().copy()
+    # ---- ply rows -----------------------------------------------------------------------------------------------------
+    gm.to_ply()
+    out["ply_rows"] = captured["rows"].astype(np.float32)
+    out["ply_names"] = np.array(captured["names"])
+    np.savez_compressed(os.path.join(HERE, "ref_training.npz"), **out)
+    print("wrote ref_training.npz:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+if __name__ == "__main__":
+    main()
