@@ -24,8 +24,8 @@ REF = "/root/reference"
 def load_reference_model():
     src = open(os.path.join(REF, "MVs_Algorithms/GaussianSplatting/main_3DGS_renderer.py")).read()
     a = src.index("def get_expon_lr_func(")
-    b = src.index("class GaussianSplattingRenderer")
-    body = src[a:b].replace('device="cuda"', 'device="cpu"').replace("device='cuda'", "device='cpu'")
+    b = len(src)                                   # GaussianModel AND GaussianSplattingRenderer
+    body = src[a:b].replace(".cuda()", "").replace('device="cuda"', 'device="cpu"').replace("device='cuda'", "device='cpu'")
     mu = open(os.path.join(REF, "mesh_processer/mesh_utils.py")).read()
     m = re.search(r"^def construct_list_of_gs_attributes\(.*?(?=^def )", mu, flags=re.S | re.M)
     captured = {}
@@ -42,6 +42,42 @@ def load_reference_model():
           "inverse_sigmoid": lambda x: torch.log(x / (1 - x)), "write_gs_ply": write_gs_ply,
           "SH2RGB": None, "RGB2SH": None, "eval_sh": None, "read_gs_ply": None, "K_nearest_neighbors_func": None,
           "math": __import__("math"), "F": torch.nn.functional}
+    # names the renderer class needs: the reference's own SH helpers, point-cloud container stubs, a recording rasterizer
+    import importlib.util, sys
+    spec = importlib.util.spec_from_file_location("ref_sh_utils_t", os.path.join(REF, "shared_utils/sh_utils.py"))
+    shu = importlib.util.module_from_spec(spec); spec.loader.exec_module(shu)
+    ns.update(SH2RGB=shu.SH2RGB, RGB2SH=shu.RGB2SH, eval_sh=shu.eval_sh)
+
+    class PointCloud:
+        def __init__(self, points, colors, normals):
+            self.points, self.colors, self.normals = points, colors, normals
+    ns.update(PointCloud=PointCloud, Mesh=type("Mesh", (), {}), PlyData=type("PlyData", (), {}))
+    knn = types.ModuleType("simple_knn"); knn_c = types.ModuleType("simple_knn._C")
+
+    def distCUDA2(points):                          # third-party (absent): stand-in = exact 3-NN mean squared distance
+        from scipy.spatial import cKDTree
+        pn = points.numpy().astype(np.float64)
+        d, _ = cKDTree(pn).query(pn, k=4)
+        return torch.from_numpy((d[:, 1:] ** 2).mean(axis=1).astype(np.float32))
+    knn_c.distCUDA2 = distCUDA2; knn._C = knn_c
+    sys.modules["simple_knn"] = knn; sys.modules["simple_knn._C"] = knn_c
+    dgr = types.ModuleType("diff_gaussian_rasterization")
+
+    class GaussianRasterizationSettings:
+        def __init__(self, **kw):
+            self.kw = kw
+
+    class GaussianRasterizer:
+        def __init__(self, raster_settings):
+            captured["settings"] = raster_settings.kw
+
+        def __call__(self, **kw):
+            captured["call"] = kw
+            n = kw["means3D"].shape[0]
+            H, W = captured["settings"]["image_height"], captured["settings"]["image_width"]
+            return torch.full((3, H, W), 1.5), torch.arange(n, dtype=torch.int32) % 3, torch.zeros(1, H, W), torch.zeros(1, H, W)
+    dgr.GaussianRasterizationSettings = GaussianRasterizationSettings; dgr.GaussianRasterizer = GaussianRasterizer
+    sys.modules["diff_gaussian_rasterization"] = dgr
     exec(m.group(0), ns)
     exec(compile(body, "ref_gaussian_model_cpu", "exec"), ns)
     return ns, captured
@@ -120,7 +156,76 @@ def main():
     out["ply_rows"] = captured["rows"].astype(np.float32)
     out["ply_names"] = np.array(captured["names"])
     np.savez_compressed(os.path.join(HERE, "ref_training.npz"), **out)
+    host_fixture(ns, captured)
     print("wrote ref_training.npz:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+def host_fixture(ns, captured):
+    """ref_host.npz: the reference's random initialisation (GaussianSplattingRenderer.initialize(None, n) +
+    GaussianModel.create_from_pcd, main_3DGS_renderer.py:798-826, 407-433), its render() host wrapper (:830-949) driven
+    with a recording rasterizer, and InstantNGP.get_rays (MVs_Algorithms/NeRF/Instant_NGP.py:37-70)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import gs_oracle as O
+    out = {}
+    n, deg = 500, 2
+    R = ns["GaussianSplattingRenderer"](sh_degree=deg, white_background=False, radius=1)
+    np.random.seed(0)
+    R.initialize(None, num_pts=n)
+    gm = R.gaussians
+    out["init_xyz"] = gm.get_xyz.detach().numpy(); out["init_features"] = gm.get_features.detach().numpy()
+    out["init_opacity"] = gm.get_opacity.detach().numpy(); out["init_scaling"] = gm.get_scaling.detach().numpy()
+    out["init_rotation"] = gm.get_rotation.detach().numpy(); out["init_spatial_lr_scale"] = np.float32(gm.spatial_lr_scale)
+    out["init_raw_opacity"] = gm._opacity.detach().numpy(); out["init_raw_scaling"] = gm._scaling.detach().numpy()
+    # render() wrapper with the reference's own MiniCam
+    cam_src = open(os.path.join(REF, "shared_utils/camera_utils.py")).read().replace(".cuda()", "")
+    cam_src = cam_src.replace("from kiui.cam import orbit_camera", "orbit_camera = None")
+    cns = {}
+    exec(compile(cam_src, "camera_utils_cpu", "exec"), cns)
+    W, H, fovy_deg = 200, 120, 49.1
+    c2w = O.orbit_camera(15, 70, 1.75)
+    fy = np.deg2rad(fovy_deg); fx = 2 * np.arctan(np.tan(fy / 2) * W / H)
+    cam = cns["MiniCam"](c2w.copy(), W, H, fy, fx, 0.01, 100.0)
+    gm.active_sh_degree = deg
+    res = R.render(cam)
+    st, call = captured["settings"], captured["call"]
+    out["render_c2w"] = c2w; out["render_dims"] = np.array([W, H, fovy_deg], dtype=np.float32)
+    for k in ("image_height", "image_width", "tanfovx", "tanfovy", "scale_modifier", "sh_degree", "prefiltered", "debug"):
+        out["set_" + k] = np.float64(st[k])
+    for k in ("bg", "viewmatrix", "projmatrix", "campos"):
+        out["set_" + k] = st[k].numpy()
+    out["call_keys"] = np.array(sorted(call.keys()))
+    out["call_none"] = np.array(sorted(k for k, v in call.items() if v is None))
+    for k in ("means3D", "means2D", "shs", "opacities", "scales", "rotations"):
+        out["call_" + k] = call[k].detach().numpy()
+    out["call_means2D_requires_grad"] = np.bool_(call["means2D"].requires_grad)
+    out["res_image_max"] = np.float32(res["image"].max())           # clamp(0,1) of the stub's 1.5
+    out["res_visibility"] = res["visibility_filter"].numpy()
+    # mesh path: OrbitCamera.perspective (camera_utils.py:128-145) and the clip transform of DiffRastRenderer.render
+    # (MVs_Algorithms/DiffRastMesh/diff_mesh_renderer.py:91-95), executed from the reference source
+    oc = cns["OrbitCamera"](1920, 1080, r=2.2, fovy=49.1, near=0.01, far=100)
+    out["gl_persp"] = oc.perspective
+    dm_src = open(os.path.join(REF, "MVs_Algorithms/DiffRastMesh/diff_mesh_renderer.py")).read()
+    lines = [l for l in dm_src.splitlines() if ("pose = torch.from_numpy" in l or "proj = torch.from_numpy" in l or "v_cam = torch.matmul" in l or "v_clip = v_cam @" in l)]
+    assert len(lines) == 4, lines
+    gv = torch.Generator().manual_seed(5)
+    v = torch.rand(64, 3, generator=gv) - 0.5
+    pose_m = O.orbit_camera(25, -40, 2.2).astype(np.float32)
+    dns = {"torch": torch, "np": np, "F": torch.nn.functional, "v": v, "pose": pose_m, "proj": oc.perspective}
+    exec("\n".join(l.strip() for l in lines), dns)
+    out["clip_v"] = v.numpy(); out["clip_pose"] = pose_m; out["clip_out"] = dns["v_clip"].numpy()
+    # Instant-NGP rays
+    ngp_src = open(os.path.join(REF, "MVs_Algorithms/NeRF/Instant_NGP.py")).read()
+    m = re.search(r"^    def get_rays\(.*?(?=^    def )", ngp_src, flags=re.S | re.M)
+    import textwrap
+    rns = {"torch": torch, "np": np, "F": torch.nn.functional,
+           "safe_normalize": lambda x, eps=1e-20: x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))}
+    exec(textwrap.dedent(m.group(0)), rns)
+    pose = torch.from_numpy(O.orbit_camera(-20, 200, 1.75).astype(np.float32))
+    ro, rd = rns["get_rays"](None, pose, 36, 50, 49.1)
+    out["rays_pose"] = pose.numpy(); out["rays_o"] = ro.numpy(); out["rays_d"] = rd.numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **out)
+    print("wrote ref_host.npz:", sorted(out.keys()))
 
 
 if __name__ == "__main__":
