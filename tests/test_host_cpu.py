@@ -38,6 +38,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.gs_b200_abi_version() == 1
 
 
+def test_every_header_is_plain_c_and_every_declared_entry_point_is_exported():
+    """include/*.h (gs, dr, ngp): each compiles as C on its own (no C++ / torch types in the boundary) and every
+    function it declares is an exported symbol of libgs_b200.so."""
+    lib = ctypes.CDLL(_ensure_built())
+    inc = os.path.join(ROOT, "include")
+    headers = sorted(f for f in os.listdir(inc) if f.endswith(".h"))
+    assert headers == ["dr_b200.h", "gs_b200.h", "ngp_b200.h"]
+    total = 0
+    for h in headers:
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, h)], check=True)
+        src = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, h)).read(), flags=re.S)
+        prefix = h.split("_")[0]
+        names = set(re.findall(r"\b(%s_b200_[a-z0-9_]+)\s*\(" % prefix, src))
+        names -= {"gs_b200_alloc_fn"}
+        assert names, h
+        for n in sorted(names):
+            assert hasattr(lib, n), f"{n} declared in include/{h} but not exported"
+        total += len(names)
+    assert total >= 45
+
+
 def test_ctypes_structs_match_header_layout():
     from gs_b200 import _lib
     code = r'''
