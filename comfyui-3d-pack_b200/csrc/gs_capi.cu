@@ -467,12 +467,12 @@ void* slot_alloc_cb(void* user, int32_t tag, size_t bytes) { return ((Slot*)user
 struct StepCache {
     Slot slot[2];
     bool init = false;
-    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr, evAux = nullptr, evPre[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
     bool busy = false;                           // a view hook must not re-enter the step entries on this thread
-    Region ws_recs, ws_sg, ws_u32, ws_spans;               // per-chunk [VB][N] arrays of the multi-view step
+    Region ws_recs[2], ws_sg[2], ws_u32[2], ws_spans[2];               // per-chunk [VB][N] arrays of the multi-view step
     int ensure_init() {
         if (init) return 0;
         for (int i = 0; i < 2; i++) {
@@ -483,6 +483,9 @@ struct StepCache {
         }
         GS_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         GS_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+        GS_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evAux, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaEventCreateWithFlags(&evPre[i], cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evD2H, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evPB, cudaEventDisableTiming));
@@ -524,40 +527,62 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     const StepOpts& O = opts ? *opts : defaults;
     if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
-    const int VB = std::min(V, std::min(gs_preprocess_multi_max_views(), 16));
-    // chunk workspace: [VB][N] arrays
+    // View chunks: one batched preprocess / preprocess-backward pass per chunk of <= 16 views, on the aux stream:
+    //   aux stream:   pre(0) | pre(1) ............ bwd(0) | pre(2) ....... bwd(1) | ... | bwd(last)
+    //   slot streams:          views of chunk 0 ........... views of chunk 1 ......
+    // pre(k+1) is enqueued when chunk k's views start, bwd(k) when they have all been enqueued; two workspace sets
+    // alternate and the aux stream's own order (bwd(k-1) before pre(k+1)) protects their reuse.
+    // GS_B200_STEP_OVERLAP=1 additionally cuts a step of >= 6 views into two chunks so that the batched passes overlap
+    // the composites instead of running alone at the head and tail of the step.  Measured on C1 (8 views): 12.25-12.33
+    // ms vs 12.09-12.10 ms without — every kernel of the step is issue-bound, so the overlapped passes only take
+    // issue slots from the composites, and the second chunk re-reads the parameters.  Off by default.
+    const int maxv = std::min(gs_preprocess_multi_max_views(), 16);
+    static const bool overlap = []() { const char* e = getenv("GS_B200_STEP_OVERLAP"); return e && e[0] == '1'; }();
+    const int nchunks = std::max((overlap && V >= 6) ? 2 : 1, (V + maxv - 1) / maxv);
+    const int VB = (V + nchunks - 1) / nchunks;
     const size_t nvb = (size_t)VB * N;
-    if (Slot::ensure(C.ws_recs, nvb * sizeof(SplatRec), user) || Slot::ensure(C.ws_sg, nvb * sizeof(SplatGrad), user) ||
-        Slot::ensure(C.ws_u32, nvb * 4 * 4 + 256 * 4, user)) return 1;
     const bool tight = g_tile_culling.load() >= 1;
-    if (tight && Slot::ensure(C.ws_spans, nvb * sizeof(uint4), user)) return 1;
-    uint4* spans_all = tight ? (uint4*)C.ws_spans.p : nullptr;
-    SplatRec* recs_all = (SplatRec*)C.ws_recs.p;
-    SplatGrad* sg_all = (SplatGrad*)C.ws_sg.p;
-    uint32_t* u32 = (uint32_t*)C.ws_u32.p;
-    int32_t* radii_all = (int32_t*)u32;
-    uint32_t* tiles_all = u32 + nvb;
-    uint32_t* dkeys_all = u32 + 2 * nvb;
-    uint32_t* ids_all = u32 + 3 * nvb;
-    uint32_t* minkeys = u32 + 4 * nvb;          // [VB] stride 2 words
+    struct WS { SplatRec* recs; SplatGrad* sg; int32_t* radii; uint32_t *tiles, *dkeys, *ids, *minkeys; uint4* spans; } ws[2];
+    const int nsets = nchunks > 1 ? 2 : 1;
+    for (int i = 0; i < nsets; i++) {
+        if (Slot::ensure(C.ws_recs[i], nvb * sizeof(SplatRec), user) || Slot::ensure(C.ws_sg[i], nvb * sizeof(SplatGrad), user) ||
+            Slot::ensure(C.ws_u32[i], nvb * 4 * 4 + 256 * 4, user)) return 1;
+        if (tight && Slot::ensure(C.ws_spans[i], nvb * sizeof(uint4), user)) return 1;
+        uint32_t* u32 = (uint32_t*)C.ws_u32[i].p;
+        ws[i] = WS{(SplatRec*)C.ws_recs[i].p, (SplatGrad*)C.ws_sg[i].p, (int32_t*)u32, u32 + nvb, u32 + 2 * nvb, u32 + 3 * nvb,
+                   u32 + 4 * nvb /* [VB] stride 2 words */, tight ? (uint4*)C.ws_spans[i].p : nullptr};
+    }
+    cudaStream_t aux = C.aux_stream;
+    // everything is ordered after the caller's stream
+    GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
+    GS_CUDA_CHECK(cudaStreamWaitEvent(aux, C.evFork, 0));
+
+    auto enqueue_pre = [&](int k) -> int {           // batched preprocess of chunk k on the aux stream
+        const int v0 = k * VB, nv = std::min(VB, V - v0);
+        const WS& w = ws[k & (nsets - 1)];
+        if (!O.forward_only) GS_CUDA_CHECK(cudaMemsetAsync(w.sg, 0, (size_t)nv * N * sizeof(SplatGrad), aux));
+        GS_CUDA_CHECK(cudaMemsetAsync(w.minkeys, 0xFF, 256 * 4, aux));
+        { StageTimer t(0, aux);
+        if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
+                                       par.shs, par.opac, par.scales, par.rots, w.recs, w.radii, w.tiles, w.dkeys, w.ids,
+                                       w.minkeys, w.spans, aux)) return 1; }
+        GS_CUDA_CHECK(cudaEventRecord(C.evPre[k & 1], aux));
+        return 0;
+    };
 
     gs_b200_state st[2];
     gs_b200_view view[2];
     std::unique_ptr<FwdCtx> ctx[2];                 // released on every exit path
     int64_t rendered = 0;
-    int rc = 0;
+    int rc = enqueue_pre(0);
 
-    for (int v0 = 0; v0 < V && !rc; v0 += VB) {
-        const int nv = std::min(VB, V - v0);
-        if (!O.forward_only) GS_CUDA_CHECK(cudaMemsetAsync(sg_all, 0, (size_t)nv * N * sizeof(SplatGrad), user));
-        GS_CUDA_CHECK(cudaMemsetAsync(minkeys, 0xFF, 256 * 4, user));
-        { StageTimer t(0, user);
-        if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
-                                       par.shs, par.opac, par.scales, par.rots, recs_all, radii_all, tiles_all,
-                                       dkeys_all, ids_all, minkeys, spans_all, user)) return 1; }
-        // fork: both slot streams continue after the preprocess
-        GS_CUDA_CHECK(cudaEventRecord(C.evFork, user));
-        for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evFork, 0));
+    for (int k = 0; k < nchunks && !rc; k++) {
+        const int v0 = k * VB, nv = std::min(VB, V - v0);
+        const WS& w = ws[k & (nsets - 1)];
+        // the slot streams continue after this chunk's preprocess ...
+        for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evPre[k & 1], 0));
+        // ... while the next chunk's preprocess already runs beside them
+        if (k + 1 < nchunks && (rc = enqueue_pre(k + 1))) break;
 
         auto launch_a = [&](int j) -> int {          // j: view index inside the chunk
             Slot& S = C.slot[j & 1];
@@ -573,10 +598,9 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
             ctx[j & 1].reset(new FwdCtx(slot_alloc_cb, &S, S.stream));
             const size_t o = (size_t)j * N;
-            PreView pre{recs_all + o, tiles_all + o, dkeys_all + o, ids_all + o, minkeys + 2 * j,
-                        spans_all ? spans_all + o : nullptr};
+            PreView pre{w.recs + o, w.tiles + o, w.dkeys + o, w.ids + o, w.minkeys + 2 * j, w.spans ? w.spans + o : nullptr};
             if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
-                            img, img + 3 * npix, img + 4 * npix, radii_all + o, &st[j & 1], S.host_total, &pre)) return 1;
+                            img, img + 3 * npix, img + 4 * npix, w.radii + o, &st[j & 1], S.host_total, &pre)) return 1;
             GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
             return S.failed ? 1 : 0;
         };
@@ -597,32 +621,39 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
                 StageTimer t(7, S.stream);
                 if ((rc = gs_launch_render_backward(ctx[j & 1]->va, (const SplatRec*)st[j & 1].geom, st[j & 1].point_list,
                                                     st[j & 1].ranges, st[j & 1].n_contrib, st[j & 1].final_T, up,
-                                                    up + 3 * npix, up + 4 * npix, sg_all + (size_t)j * N, S.stream))) break;
+                                                    up + 3 * npix, up + 4 * npix, w.sg + (size_t)j * N, S.stream))) break;
             }
             if (S.failed) { rc = 1; break; }
         }
         for (int i = 0; i < 2; i++) ctx[i].reset();
-        // join: the caller's stream continues after both slot streams
+        // the aux stream picks up after this chunk's views (batched backward, radii copy, workspace hand-over)
         for (int i = 0; i < 2; i++) {
             cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
-            cudaStreamWaitEvent(user, C.slot[i].evDone, 0);
+            cudaStreamWaitEvent(aux, C.slot[i].evDone, 0);
         }
         if (rc) break;
-        if (O.radii_out) GS_CUDA_CHECK(cudaMemcpyAsync(O.radii_out + (size_t)v0 * N, radii_all, (size_t)nv * N * 4, cudaMemcpyDeviceToDevice, user));
+        if (O.radii_out) GS_CUDA_CHECK(cudaMemcpyAsync(O.radii_out + (size_t)v0 * N, w.radii, (size_t)nv * N * 4, cudaMemcpyDeviceToDevice, aux));
         if (O.forward_only) continue;
-        const bool last_chunk = v0 + VB >= V;
+        const bool last_chunk = k + 1 == nchunks;
         const int nparts = (sink && last_chunk && sink->nchunks > 1) ? sink->nchunks : 1;
         const int per = (((N + nparts - 1) / nparts) + 127) / 128 * 128;
         for (int first = 0; first < N && !rc; first += per) {
             const int count = std::min(per, N - first);
-            { StageTimer t(8, user);
+            { StageTimer t(8, aux);
             rc = gs_launch_preprocess_backward_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M,
-                                                     par.means, par.shs, par.scales, par.rots, radii_all, sg_all, grd.means,
-                                                     grd.m2d, grd.shs, grd.opac, grd.scales, grd.rots, v0 > 0 ? 1 : 0, first,
-                                                     count, user); }
-            if (!rc && sink && last_chunk) sink->fn(sink->ctx, first, count, user);
+                                                     par.means, par.shs, par.scales, par.rots, w.radii, w.sg, grd.means,
+                                                     grd.m2d, grd.shs, grd.opac, grd.scales, grd.rots, k > 0 ? 1 : 0, first,
+                                                     count, aux); }
+            if (!rc && sink && last_chunk) sink->fn(sink->ctx, first, count, aux);
         }
     }
+    // join: the caller's stream continues after the aux stream (which has waited for both slot streams)
+    for (int i = 0; i < 2; i++) {          // (on an error path the slots may not have been joined into aux yet)
+        cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
+        cudaStreamWaitEvent(aux, C.slot[i].evDone, 0);
+    }
+    cudaEventRecord(C.evAux, aux);
+    cudaStreamWaitEvent(user, C.evAux, 0);
     if (num_rendered_out) *num_rendered_out = rendered;
     return rc;
 }
