@@ -212,8 +212,22 @@ def test_inference_mode_and_reference_render_wrapper_contract(R, dev):
     assert float((alpha.cpu() - refa).abs().max()) < RGBA_ATOL
 
 
-def test_knn_mean_dist2_matches_kdtree(R, dev):
-    pts = O.make_cloud("D0", 5000, 0, seed=2)["means3D"]
+@pytest.mark.parametrize("kind,n", [("ball", 5000), ("ball", 60000), ("clusters", 40000), ("plane", 30000), ("dups", 20000)])
+def test_knn_mean_dist2_matches_kdtree(R, dev, kind, n):
+    """distCUDA2 replacement: all-pairs kernel below 8192 points, exact grid search above; both against a kd-tree."""
+    g = torch.Generator().manual_seed(n)
+    if kind == "ball":
+        pts = O.make_cloud("D0", n, 0, seed=2)["means3D"]
+    elif kind == "clusters":          # very uneven density: 20 tight blobs + a sparse background
+        c = torch.rand(20, 3, generator=g) * 4 - 2
+        pts = torch.cat([c[torch.randint(0, 20, (n - 500,), generator=g)] + 0.01 * torch.randn(n - 500, 3, generator=g),
+                         torch.rand(500, 3, generator=g) * 20 - 10])
+    elif kind == "plane":             # zero extent along z
+        pts = torch.cat([torch.rand(n, 2, generator=g), torch.zeros(n, 1)], dim=1)
+    else:                             # exact duplicates: distance 0 neighbours
+        base = torch.rand(n // 4, 3, generator=g)
+        pts = base.repeat(4, 1)[torch.randperm(n // 4 * 4, generator=g)]
+    pts = pts.float().contiguous()
     got = R.knn_mean_dist2(pts.to(dev)).cpu().numpy()
     ref = O.knn_mean_dist2(pts.numpy())
     assert np.allclose(got, ref, rtol=1e-4, atol=1e-9)
