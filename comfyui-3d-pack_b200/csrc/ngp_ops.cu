@@ -63,14 +63,29 @@ grid_encode_fwd_kernel(const float* __restrict__ x, long long N, const float2* _
 // bit 0 (always for even cell x in the hashed levels: (x+1)^h == (x^h)^1 and the table size is a power of two; for
 // even linear indices in the dense levels) -> one red.global.add.v4.f32 instead of two .v2 (L2 atomic units are
 // the bound of this kernel: profiles/r1_ngp_kernels.txt).
+// one x-neighbour corner pair (values a = corner x, b = corner x+1) -> one .v4 red or two .v2 reds
+template <bool V4>
+__device__ __forceinline__ void red_pair(float2* __restrict__ table, uint32_t i0, uint32_t i1, float2 a, float2 b) {
+    if (V4 && (i0 ^ i1) == 1u) {
+        const bool lo0 = (i0 & 1u) == 0u;                  // which of the two is the even (lower) entry
+        const float2 lo = lo0 ? a : b, hi = lo0 ? b : a;
+        atomicAdd(reinterpret_cast<float4*>(table + (i0 & ~1u)), make_float4(lo.x, lo.y, hi.x, hi.y));
+    } else {
+        atomicAdd(table + i0, a);                          // red.global.add.v2.f32
+        atomicAdd(table + i1, b);
+    }
+}
+
+// levels [l0, L): thread = (sample, level), adjacent threads = adjacent levels of one sample
 template <bool V4>
 __global__ void __launch_bounds__(256)
-grid_encode_bwd_kernel(const float* __restrict__ x, long long N, GridMeta gm, const float2* __restrict__ g_out,
+grid_encode_bwd_kernel(const float* __restrict__ x, long long N, GridMeta gm, int l0, const float2* __restrict__ g_out,
                        float2* __restrict__ d_emb) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * gm.L) return;
-    const long long n = gid / gm.L; const int l = (int)(gid - n * gm.L);
-    const float2 g = g_out[gid];
+    const int nl = gm.L - l0;
+    if (gid >= N * nl) return;
+    const long long n = gid / nl; const int l = l0 + (int)(gid - n * nl);
+    const float2 g = g_out[n * gm.L + l];
     if (g.x == 0.f && g.y == 0.f) return;
     uint32_t pg[3]; float fr[3];
     cell_of(x, n, gm, l, pg, fr);
@@ -83,14 +98,60 @@ grid_encode_bwd_kernel(const float* __restrict__ x, long long N, GridMeta gm, co
         const float w0 = (1.f - fr[0]) * wyz, w1 = fr[0] * wyz;
         const uint32_t i0 = grid_index(pg[0], pg[1] + by, pg[2] + bz, gm.res[l], hsize);
         const uint32_t i1 = grid_index(pg[0] + 1, pg[1] + by, pg[2] + bz, gm.res[l], hsize);
-        if (V4 && (i0 ^ i1) == 1u) {
-            const bool lo0 = (i0 & 1u) == 0u;              // which of the two is the even (lower) entry
-            const float wa = lo0 ? w0 : w1, wb = lo0 ? w1 : w0;
-            atomicAdd(reinterpret_cast<float4*>(table + (i0 & ~1u)), make_float4(wa * g.x, wa * g.y, wb * g.x, wb * g.y));
-        } else {
-            atomicAdd(table + i0, make_float2(w0 * g.x, w0 * g.y));   // red.global.add.v2.f32
-            atomicAdd(table + i1, make_float2(w1 * g.x, w1 * g.y));
+        red_pair<V4>(table, i0, i1, make_float2(w0 * g.x, w0 * g.y), make_float2(w1 * g.x, w1 * g.y));
+    }
+}
+
+// Coarse levels [0, l0) (cell much larger than the marching step): consecutive samples of a ray fall into the SAME cell
+// for long runs (25 samples at resolution 16 with dt = 5e-3), i.e. hit the same 8 table entries.  Here a warp takes
+// 32 consecutive samples of ONE level, sums the 16 corner contributions over each run of equal cells with a segmented
+// shuffle reduction, and only the head lane of a run issues the reds: the kernel is bound by L2 atomic operations
+// (profiles/r1_ngp_kernels.txt), the shuffles ride in otherwise idle issue slots.
+template <bool V4>
+__global__ void __launch_bounds__(256)
+grid_encode_bwd_runs_kernel(const float* __restrict__ x, long long N, GridMeta gm, const float2* __restrict__ g_out,
+                            float2* __restrict__ d_emb) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y, lane = threadIdx.x & 31;
+    const bool live = n < N;
+    float2 g = make_float2(0.f, 0.f);
+    uint32_t pg[3] = {0u, 0u, 0u}; float fr[3] = {0.f, 0.f, 0.f};
+    if (live) { g = g_out[n * gm.L + l]; cell_of(x, n, gm, l, pg, fr); }
+    const uint32_t key = live ? (pg[0] | (pg[1] << 10) | (pg[2] << 20)) : 0xFFFFFFFFu;      // res + 1 <= 1024 here
+    float vx[8], vy[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint32_t bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
+        const float w = (bx ? fr[0] : 1.f - fr[0]) * ((by ? fr[1] : 1.f - fr[1]) * (bz ? fr[2] : 1.f - fr[2]));
+        vx[c] = w * g.x; vy[c] = w * g.y;
+    }
+    const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+    const bool head = (lane == 0) || (key != prev);
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+    const int run = __popc(heads & (0xFFFFFFFFu >> (31 - lane)));
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int orun = __shfl_down_sync(0xFFFFFFFFu, run, off);
+        const bool take = (lane + off < 32) && (orun == run);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float ox = __shfl_down_sync(0xFFFFFFFFu, vx[c], off), oy = __shfl_down_sync(0xFFFFFFFFu, vy[c], off);
+            if (take) { vx[c] += ox; vy[c] += oy; }
         }
+    }
+    if (!head || !live) return;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 8; c++) any = any || (vx[c] != 0.f) || (vy[c] != 0.f);
+    if (!any) return;
+    const uint32_t hsize = (uint32_t)(gm.off[l + 1] - gm.off[l]);
+    float2* table = d_emb + gm.off[l];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint32_t by = c & 1, bz = (c >> 1) & 1;
+        const uint32_t i0 = grid_index(pg[0], pg[1] + by, pg[2] + bz, gm.res[l], hsize);
+        const uint32_t i1 = grid_index(pg[0] + 1, pg[1] + by, pg[2] + bz, gm.res[l], hsize);
+        red_pair<V4>(table, i0, i1, make_float2(vx[2 * c], vy[2 * c]), make_float2(vx[2 * c + 1], vy[2 * c + 1]));
     }
 }
 
@@ -294,10 +355,23 @@ int ngp_grid_encode_bwd(const float* x, long long N, const int32_t* offsets_host
                         const float* g_out, float* d_emb, cudaStream_t s) {
     if (N <= 0) return 0;
     GridMeta gm; if (make_meta(gm, offsets_host, L, bound, pls, base)) return 1;
-    static const bool v4 = []() { const char* e = getenv("NGP_B200_RED_V4"); return !(e && e[0] == '0'); }();
-    if (v4 && ((uintptr_t)d_emb & 15) == 0) grid_encode_bwd_kernel<true><<<NGP_GRID(N * L), 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
-    else grid_encode_bwd_kernel<false><<<NGP_GRID(N * L), 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
-    gs_count_launches(1);
+    static const bool v4env = []() { const char* e = getenv("NGP_B200_RED_V4"); return !(e && e[0] == '0'); }();
+    static const bool runs = []() { const char* e = getenv("NGP_B200_BWD_RUNS"); return !(e && e[0] == '0'); }();
+    const bool v4 = v4env && ((uintptr_t)d_emb & 15) == 0;
+    // coarse levels (resolution <= 128: runs of >= ~3 samples per cell at the reference's 5e-3 step) go through the
+    // run-reducing kernel; they are the first levels since resolutions grow with the level index
+    int l0 = 0;
+    if (runs) while (l0 < L && gm.res[l0] <= 128 && l0 < 8) l0++;
+    if (l0 > 0) {
+        const dim3 grid((unsigned)((N + 255) / 256), (unsigned)l0);
+        if (v4) grid_encode_bwd_runs_kernel<true><<<grid, 256, 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
+        else grid_encode_bwd_runs_kernel<false><<<grid, 256, 0, s>>>(x, N, gm, (const float2*)g_out, (float2*)d_emb);
+    }
+    if (l0 < L) {
+        if (v4) grid_encode_bwd_kernel<true><<<NGP_GRID(N * (L - l0)), 0, s>>>(x, N, gm, l0, (const float2*)g_out, (float2*)d_emb);
+        else grid_encode_bwd_kernel<false><<<NGP_GRID(N * (L - l0)), 0, s>>>(x, N, gm, l0, (const float2*)g_out, (float2*)d_emb);
+    }
+    gs_count_launches((l0 > 0) + (l0 < L));
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
