@@ -224,8 +224,94 @@ def host_fixture(ns, captured):
     pose = torch.from_numpy(O.orbit_camera(-20, 200, 1.75).astype(np.float32))
     ro, rd = rns["get_rays"](None, pose, 36, 50, 49.1)
     out["rays_pose"] = pose.numpy(); out["rays_o"] = ro.numpy(); out["rays_d"] = rd.numpy()
+    ngp_fixture(out, O)
     np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **out)
     print("wrote ref_host.npz:", sorted(out.keys()))
+
+
+def ngp_fixture(out, O):
+    """InstantNGP.render_nerf (MVs_Algorithms/NeRF/Instant_NGP.py:101-156) executed from the reference source with its
+    third-party imports (nerfacc, kiui — absent) served by oracle/ngp_oracle.py: pins the CALL SEQUENCE and composition
+    (ray generation, density-driven sampling, sample midpoints, the two field queries, weights, accumulation, background)
+    that tests/test_gpu_ngp.py::test_render_nerf_call_sequence_matches_oracle replays.  Parameters are regenerated in the
+    test from the stored seed (tables are tens of MB)."""
+    import sys
+    from torch import nn
+    from oracle import ngp_oracle as NO
+
+    class GridEncoder(nn.Module):
+        def __init__(self, num_levels=16):
+            super().__init__()
+            self.num_levels = num_levels
+            self.offsets = NO.grid_offsets(num_levels=num_levels)
+            self.embeddings = nn.Parameter(torch.zeros(int(self.offsets[-1]), 2))
+            self.output_dim = 2 * num_levels
+
+        def forward(self, xs, bound=1):
+            return NO.grid_encode(xs, self.embeddings, self.offsets, bound=float(bound), num_levels=self.num_levels)
+
+    class MLP(nn.Module):
+        def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True):
+            super().__init__()
+            self.net = nn.ModuleList([nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=bias)
+                                      for l in range(num_layers)])
+
+        def forward(self, x):
+            for l, lin in enumerate(self.net):
+                x = lin(x)
+                if l != len(self.net) - 1:
+                    x = torch.relu(x)
+            return x
+
+    class OccGridEstimator(nn.Module):
+        def __init__(self, roi_aabb, resolution=64, levels=1):
+            super().__init__()
+            self.aabb = roi_aabb; self.binaries = torch.zeros(1, resolution, resolution, resolution, dtype=torch.bool)
+
+        def sampling(self, rays_o, rays_d, sigma_fn=None, near_plane=0.0, far_plane=1e10, render_step_size=1e-3, stratified=False, cone_angle=0.0):
+            assert not stratified and cone_angle == 0
+            ri, t0, t1 = NO.march(rays_o, rays_d, self.binaries[0], self.aabb, near_plane, far_plane, render_step_size)
+            if sigma_fn is not None and ri.numel():
+                sig = sigma_fn(t0, t1, ri)
+                m = NO.visibility_mask(t0, t1, sig, ri, rays_o.shape[0], 1e-4, 0.0)
+                ri, t0, t1 = ri[m], t0[m], t1[m]
+            return ri, t0, t1
+    mods = {}
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; mods[name] = m; return m
+    mod("nerfacc", OccGridEstimator=OccGridEstimator,
+        render_weight_from_density=lambda t_starts, t_ends, sigmas, ray_indices=None, n_rays=None: NO.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices, n_rays),
+        accumulate_along_rays=lambda weights, values=None, ray_indices=None, n_rays=None: NO.accumulate_along_rays(weights, values, ray_indices, n_rays))
+    mod("comfy"); mod("comfy.utils")
+    mod("pytorch_msssim", SSIM=object, MS_SSIM=object)
+    mod("kiui"); mod("kiui.op", safe_normalize=lambda x, eps=1e-20: x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps)))
+    mod("kiui.cam", orbit_camera=O.orbit_camera); mod("kiui.nn", MLP=MLP, trunc_exp=NO.trunc_exp); mod("kiui.gridencoder", GridEncoder=GridEncoder)
+    mod("shared_utils"); mod("shared_utils.image_utils", prepare_torch_img=None)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_instant_ngp", os.path.join(REF, "MVs_Algorithms/NeRF/Instant_NGP.py"))
+    ngp = importlib.util.module_from_spec(spec); spec.loader.exec_module(ngp)
+    res, seed = 20, 4321
+    model = ngp.InstantNGP(resolution=res, device="cpu")
+    model.ref_cam_fovy = 49.1
+    model.eval()
+    torch.manual_seed(seed)                      # parameter order below is what the test reproduces
+    for enc in (model.encoder_density, model.encoder):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    for mlp in (model.mlp_density, model.mlp):
+        for lin in mlp.net:
+            lin.weight.data.uniform_(-0.4, 0.4)
+    R = 64
+    gg = (torch.arange(R).float() + 0.5) / R * 2 - 1
+    x, y, z = torch.meshgrid(gg, gg, gg, indexing="ij")
+    model.estimator.binaries = ((x * x + y * y + z * z) < 0.36)[None]
+    pose = O.orbit_camera(10, 140, 1.75).astype(np.float32)
+    with torch.no_grad():
+        color, alpha = model.render_nerf(pose, bg_color=1)
+    out["ngp_seed"] = np.int64(seed); out["ngp_res"] = np.int64(res); out["ngp_pose"] = pose
+    out["ngp_color"] = color.numpy(); out["ngp_alpha"] = alpha.numpy()
+    out["ngp_levels"] = np.int64(model.encoder.num_levels); out["ngp_mlp_in"] = np.int64(model.encoder.output_dim)
+    for k in list(mods):
+        sys.modules.pop(k, None)
 
 
 if __name__ == "__main__":
