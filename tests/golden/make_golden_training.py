@@ -225,8 +225,48 @@ def host_fixture(ns, captured):
     ro, rd = rns["get_rays"](None, pose, 36, 50, 49.1)
     out["rays_pose"] = pose.numpy(); out["rays_o"] = ro.numpy(); out["rays_d"] = rd.numpy()
     ngp_fixture(out, O)
+    mesh_fixture(out, O)
     np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **out)
     print("wrote ref_host.npz:", sorted(out.keys()))
+
+
+def mesh_fixture(out, O):
+    """DiffRastRenderer.render (MVs_Algorithms/DiffRastMesh/diff_mesh_renderer.py:72-159) executed from the reference
+    source with `nvdiffrast.torch` served by oracle/dr_oracle.py: pins the op order and composition of the mesh path
+    (clip transform, rasterize, antialias(alpha), interpolate(uv, 'all'), texture('linear') + sigmoid, depth and normal
+    interpolation, antialias(colour), background blend) that tests/test_gpu_mesh.py replays against the shim."""
+    import sys, importlib.util
+    from oracle import dr_oracle as DO
+    mods = {}
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; mods[name] = m; return m
+    nv = mod("nvdiffrast")
+    drt = mod("nvdiffrast.torch", RasterizeCudaContext=lambda *a, **k: object(), RasterizeGLContext=lambda *a, **k: object(),
+              rasterize=lambda ctx, pos, tri, resolution: DO.rasterize(pos, tri, tuple(resolution)),
+              interpolate=lambda attr, rast, tri, rast_db=None, diff_attrs=None: DO.interpolate(attr, rast, tri, rast_db=rast_db, diff_attrs=diff_attrs),
+              texture=lambda tex, uv, uv_da=None, filter_mode="auto": DO.texture(tex, uv, filter_mode="linear"),
+              antialias=lambda color, rast, pos, tri: DO.antialias(color, rast, pos, tri))
+    nv.torch = drt
+    sn = lambda x, eps=1e-20: x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))
+    mod("kiui"); mod("kiui.op", inverse_sigmoid=lambda x: torch.log(x / (1 - x)))
+    mod("mesh_processer"); mod("mesh_processer.mesh", safe_normalize=sn)
+    spec = importlib.util.spec_from_file_location("ref_diff_mesh_renderer", os.path.join(REF, "MVs_Algorithms/DiffRastMesh/diff_mesh_renderer.py"))
+    dm = importlib.util.module_from_spec(spec); spec.loader.exec_module(dm)
+    v, f, uv = DO.icosphere(2, 0.5)
+    g = torch.Generator().manual_seed(11)
+    albedo = torch.rand(16, 16, 3, generator=g) * 0.8 + 0.1
+    mesh = types.SimpleNamespace(v=v, f=f, vt=uv, ft=f, vn=sn(v), fn=f, albedo=albedo)
+    R = dm.DiffRastRenderer(mesh, True)
+    Hh, Ww = 40, 48
+    pose = O.orbit_camera(20, 35, 1.75).astype(np.float32)
+    proj = DO.gl_perspective(49.1, Ww / Hh)
+    with torch.no_grad():
+        res = R.render(pose, proj, Hh, Ww, ssaa=1, bg_color=1)
+    out["mesh_pose"] = pose; out["mesh_proj"] = proj; out["mesh_hw"] = np.array([Hh, Ww]); out["mesh_albedo"] = albedo.numpy()
+    for k in ("image", "alpha", "depth", "normal", "viewcos"):
+        out["mesh_" + k] = res[k].numpy()
+    for k in list(mods):
+        sys.modules.pop(k, None)
 
 
 def ngp_fixture(out, O):
