@@ -157,7 +157,117 @@ def main():
     out["ply_names"] = np.array(captured["names"])
     np.savez_compressed(os.path.join(HERE, "ref_training.npz"), **out)
     host_fixture(ns, captured)
+    loop_fixture(ns)
     print("wrote ref_training.npz:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+def loop_fixture(ns):
+    """ref_loop.npz: GaussianSplatting3D.training (MVs_Algorithms/GaussianSplatting/main_3DGS.py:129-232) executed from the
+    reference source for a few steps on the CPU — its own GaussianModel / renderer / camera controller / loss composition
+    / Adam — with the absent third-party pieces served by this repo's checkers: `diff_gaussian_rasterization` by
+    oracle/gs_oracle.py (autograd), `pytorch_msssim.MS_SSIM` by gs_b200/losses.py, `kiui.cam.orbit_camera` by the
+    oracle's.  Stored: the state before the loop, per step the reference image index / camera record / background the
+    loop drew, and the raw parameters after every optimizer step.  tests/test_gpu_trainer.py replays it on the GPU."""
+    import sys, random as _random, tqdm as _tqdm
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "comfyui-3d-pack_b200"))
+    from oracle import gs_oracle as O
+    from gs_b200 import losses as L
+    log = {"bg": [], "view": [], "proj": [], "campos": [], "tan": [], "idx": []}
+    dgr = types.ModuleType("diff_gaussian_rasterization")
+
+    class GaussianRasterizationSettings:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+
+    class GaussianRasterizer:
+        def __init__(self, raster_settings):
+            self.rs = raster_settings
+
+        def __call__(self, means3D, means2D, shs=None, colors_precomp=None, opacities=None, scales=None, rotations=None, cov3D_precomp=None):
+            r = self.rs
+            st = O.Settings(image_height=r.image_height, image_width=r.image_width, tanfovx=r.tanfovx, tanfovy=r.tanfovy, bg=r.bg,
+                            scale_modifier=r.scale_modifier, viewmatrix=r.viewmatrix, projmatrix=r.projmatrix, sh_degree=r.sh_degree,
+                            campos=r.campos)
+            log["bg"].append(r.bg.numpy().copy()); log["view"].append(r.viewmatrix.numpy().copy()); log["proj"].append(r.projmatrix.numpy().copy())
+            log["campos"].append(r.campos.numpy().copy()); log["tan"].append(np.array([r.tanfovx, r.tanfovy], dtype=np.float32))
+            return O.rasterize(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, st)
+    dgr.GaussianRasterizationSettings = GaussianRasterizationSettings; dgr.GaussianRasterizer = GaussianRasterizer
+    sys.modules["diff_gaussian_rasterization"] = dgr
+    # camera utilities from the reference source
+    cam_src = open(os.path.join(REF, "shared_utils/camera_utils.py")).read().replace(".cuda()", "").replace("device='cuda'", "device='cpu'")
+    cam_src = cam_src.replace("from kiui.cam import orbit_camera", "orbit_camera = None")
+    cns = {}
+    exec(compile(cam_src, "camera_utils_cpu", "exec"), cns)
+    cns["orbit_camera"] = O.orbit_camera
+    img_src = open(os.path.join(REF, "shared_utils/image_utils.py")).read()
+    m = re.search(r"^def prepare_torch_img\(.*?(?=^def )", img_src, flags=re.S | re.M)
+    ins = {"torch": torch, "F": torch.nn.functional}
+    exec(m.group(0).replace('device="cuda"', 'device="cpu"'), ins)
+
+    class MS_SSIM:
+        def __init__(self, data_range=1, size_average=True, channel=3):
+            assert data_range == 1 and size_average and channel == 3
+
+        def __call__(self, X, Y):
+            return L.ms_ssim(X, Y)
+
+    class _Rand:                                    # records the view index the loop draws
+        def randint(self, a, b):
+            i = _random.randint(a, b); log["idx"].append(i); return i
+
+    class _Ev:
+        def __init__(self, *a, **k): pass
+        def record(self): pass
+    comfy = types.SimpleNamespace(utils=types.SimpleNamespace(ProgressBar=lambda n: types.SimpleNamespace(update_absolute=lambda i: None)))
+    src = open(os.path.join(REF, "MVs_Algorithms/GaussianSplatting/main_3DGS.py")).read()
+    body = src[src.index("class GSParams"):]
+    body = body.replace("device='cuda'", "device='cpu'").replace(".cuda()", "")
+    body = body.replace("torch.cuda.Event(enable_timing=True)", "_Ev()").replace("torch.cuda.synchronize()", "None")
+    mns = {"random": _Rand(), "tqdm": _tqdm, "torch": torch, "F": torch.nn.functional, "MS_SSIM": MS_SSIM, "SSIM": None, "comfy": comfy,
+           "GaussianSplattingRenderer": ns["GaussianSplattingRenderer"], "BaseCameraController": cns["BaseCameraController"],
+           "MiniCam": cns["MiniCam"], "calculate_fovX": cns["calculate_fovX"], "get_projection_matrix": cns["get_projection_matrix"],
+           "prepare_torch_img": ins["prepare_torch_img"], "_Ev": _Ev}
+    exec(compile(body, "ref_main_3dgs_cpu", "exec"), mns)
+    K, N, deg, Hh, Ww = 5, 300, 1, 176, 176
+    _random.seed(5); np.random.seed(0); torch.manual_seed(0)
+    gsp = mns["GSParams"](training_iterations=K, batch_size=1, num_pts=N, sh_degree=deg, density_start_iter=10 ** 9)
+    T = mns["GaussianSplatting3D"](gs_params=gsp, init_input=None, device="cpu")
+    gm = T.renderer.gaussians
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():                           # a trained-like state: anisotropic, coloured, varied opacity
+        gm._scaling.add_(torch.randn(N, 3, generator=g) * 0.4 + 0.8)
+        gm._rotation.copy_(torch.randn(N, 4, generator=g))
+        gm._features_dc.copy_(torch.randn(N, 1, 3, generator=g))
+        gm._features_rest.copy_(torch.randn(N, (deg + 1) ** 2 - 1, 3, generator=g) * 0.1)
+        gm._opacity.copy_(torch.randn(N, 1, generator=g))
+    out = {"N": np.int64(N), "deg": np.int64(deg), "HW": np.array([Hh, Ww]), "K": np.int64(K)}
+    for k, v in (("xyz", gm._xyz), ("f_dc", gm._features_dc), ("f_rest", gm._features_rest), ("scaling", gm._scaling),
+                 ("rotation", gm._rotation), ("opacity", gm._opacity)):
+        out["init_" + k] = v.detach().numpy().copy()
+    n_ref = 3
+    ref_imgs = [torch.rand(Hh, Ww, 3, generator=g) for _ in range(n_ref)]
+    ref_masks = [(torch.rand(Hh, Ww, generator=g) > 0.35).float() for _ in range(n_ref)]
+    poses = [(1.75, 10.0 * i - 10.0, 120.0 * i, 0.0, 0.0, 0.0) for i in range(n_ref)]          # radius, elevation, azimuth, centre
+    T.prepare_training(ref_imgs, ref_masks, poses, 49.1)
+    out["ref_imgs"] = T.ref_imgs_torch.numpy().copy(); out["ref_masks"] = T.ref_masks_torch.numpy().copy()
+    snaps = []
+    opt = T.optimizer
+    orig_step = opt.step
+
+    def step_and_snapshot(*a, **k):
+        r = orig_step(*a, **k)
+        snaps.append({grp["name"]: grp["params"][0].detach().numpy().copy() for grp in opt.param_groups})
+        return r
+    opt.step = step_and_snapshot
+    T.training()
+    assert len(snaps) == K and len(log["idx"]) == K and len(log["bg"]) == K
+    out["idx"] = np.array(log["idx"], dtype=np.int64)
+    for k in ("bg", "view", "proj", "campos", "tan"):
+        out["step_" + k] = np.stack(log[k])
+    for kname in ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"):
+        out["after_" + kname] = np.stack([sn[kname] for sn in snaps])
+    np.savez_compressed(os.path.join(HERE, "ref_loop.npz"), **out)
+    print("wrote ref_loop.npz: idx", out["idx"], "bg", out["step_bg"][:, 0], "max |dxyz|", float(np.abs(out["after_xyz"][-1] - out["init_xyz"]).max()))
 
 
 def host_fixture(ns, captured):
