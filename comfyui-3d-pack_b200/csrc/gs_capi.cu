@@ -495,7 +495,7 @@ struct StepCache {
 };
 thread_local StepCache g_step;
 
-struct PackedPtrs { float *means, *shs, *opac, *scales, *rots, *m2d; };
+struct PackedPtrs { float *means, *shs, *opac, *scales, *rots, *m2d; float* colors = nullptr; /* [N,3] instead of shs: forward-only */ };
 PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
     PackedPtrs p;
     p.means = base; p.shs = p.means + N * 3; p.opac = p.shs + N * 3 * M; p.scales = p.opac + N;
@@ -564,7 +564,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
         GS_CUDA_CHECK(cudaMemsetAsync(w.minkeys, 0xFF, 256 * 4, aux));
         { StageTimer t(0, aux);
         if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
-                                       par.shs, par.opac, par.scales, par.rots, w.recs, w.radii, w.tiles, w.dkeys, w.ids,
+                                       par.shs, par.colors, par.opac, par.scales, par.rots, w.recs, w.radii, w.tiles, w.dkeys, w.ids,
                                        w.minkeys, w.spans, aux)) return 1; }
         GS_CUDA_CHECK(cudaEventRecord(C.evPre[k & 1], aux));
         return 0;
@@ -599,7 +599,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
             ctx[j & 1].reset(new FwdCtx(slot_alloc_cb, &S, S.stream));
             const size_t o = (size_t)j * N;
             PreView pre{w.recs + o, w.tiles + o, w.dkeys + o, w.ids + o, w.minkeys + 2 * j, w.spans ? w.spans + o : nullptr};
-            if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, nullptr, par.opac, par.scales, par.rots, nullptr,
+            if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, par.colors, par.opac, par.scales, par.rots, nullptr,
                             img, img + 3 * npix, img + 4 * npix, w.radii + o, &st[j & 1], S.host_total, &pre)) return 1;
             GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
             return S.failed ? 1 : 0;
@@ -816,13 +816,14 @@ int32_t gs_b200_step_device_train(int32_t V, int32_t H, int32_t W, int32_t sh_de
 
 int32_t gs_b200_render_views(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
                              const float* views_host, const float* views_dev, int32_t N, int32_t M,
-                             const float* means3D, const float* shs, const float* opacities, const float* scales,
-                             const float* rotations, float* images, int32_t* radii, int64_t* num_rendered_out,
-                             void* stream_) {
+                             const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                             const float* scales, const float* rotations, float* images, int32_t* radii,
+                             int64_t* num_rendered_out, void* stream_) {
     cudaStream_t s = (cudaStream_t)stream_;
-    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !shs || !opacities || !scales || !rotations ||
-        !images) { gs_set_error("render_views: bad argument"); return 1; }
-    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.opac = (float*)opacities;
+    if (V <= 0 || N <= 0 || !views_host || !views_dev || !means3D || !opacities || !scales || !rotations || !images) {
+        gs_set_error("render_views: bad argument"); return 1; }
+    if ((shs == nullptr) == (colors_precomp == nullptr)) { gs_set_error("Please provide excatly one of either SHs or precomputed colors!"); return 1; }
+    PackedPtrs par; par.means = (float*)means3D; par.shs = (float*)shs; par.colors = (float*)colors_precomp; par.opac = (float*)opacities;
     par.scales = (float*)scales; par.rots = (float*)rotations; par.m2d = nullptr;
     PackedPtrs grd{};
     StepOpts o; o.forward_only = true; o.radii_out = radii;

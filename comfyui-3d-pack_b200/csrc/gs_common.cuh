@@ -149,10 +149,10 @@ int gs_launch_preprocess_backward(const ViewArgs& va, int N, int M, const float*
 
 int gs_preprocess_multi_max_views();
 int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int sh_degree, float scale_modifier, int N,
-                               int M, const float* means3D, const float* shs, const float* opacities,
-                               const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
-                               uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
-                               uint4* spans, cudaStream_t s);
+                               int M, const float* means3D, const float* shs, const float* colors_precomp,
+                               const float* opacities, const float* scales, const float* rotations, SplatRec* recs,
+                               int32_t* radii, uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids,
+                               uint32_t* min_keys, uint4* spans, cudaStream_t s);
 int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, int H, int sh_degree,
                                         float scale_modifier, int N, int M, const float* means3D, const float* shs,
                                         const float* scales, const float* rotations, const int32_t* radii,

@@ -260,6 +260,7 @@ constexpr int PP_MAXV = 16;
 __global__ void __launch_bounds__(PP_THREADS)
 preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, int sh_degree, float scale_modifier,
                         int N, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                        const float* __restrict__ colors_precomp /* [N,3] instead of shs (forward-only callers) */,
                         const float* __restrict__ opacities, const float* __restrict__ scales,
                         const float* __restrict__ rotations, SplatRec* __restrict__ recs,
                         int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
@@ -274,12 +275,13 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
     if (tid < V) s_min[tid] = 0xFFFFFFFFu;
     const int row = 3 * M;
     const int rowp = gs_rowp(row);
-    gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
+    if (shs != nullptr) gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
     __syncthreads();
     const bool live = base + tid < N;
     const int idx = live ? base + tid : N - 1;
     const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
     const float opacity = opacities[idx];
+    const float* col = colors_precomp ? colors_precomp + 3 * (size_t)idx : nullptr;
     float c[6];
     cov3d_of(scales, rotations, nullptr, scale_modifier, idx, c);
     const int tiles_x = (W + GS_TILE - 1) / GS_TILE, tiles_y = (H + GS_TILE - 1) / GS_TILE;
@@ -288,7 +290,7 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
         const float tfx = vw[38], tfy = vw[39];
         ViewK vk{vw, vw + 16, vw + 32, tfx, tfy, (float)W / (2.0f * tfx), (float)H / (2.0f * tfy), W, H, tiles_x, tiles_y};
         SplatRec rec; int my_radius; uint32_t tiles, dkey; uint4 sp;
-        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, nullptr, rec, my_radius, tiles, dkey,
+        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, col, rec, my_radius, tiles, dkey,
                      spans != nullptr, sp);
         if (live) {
             const size_t o = (size_t)v * N + idx;
@@ -329,18 +331,19 @@ int gs_launch_preprocess(const ViewArgs& va, int N, int M, const float* means3D,
 int gs_preprocess_multi_max_views() { return PP_MAXV; }
 
 int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int sh_degree, float scale_modifier, int N,
-                               int M, const float* means3D, const float* shs, const float* opacities,
-                               const float* scales, const float* rotations, SplatRec* recs, int32_t* radii,
-                               uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids, uint32_t* min_keys,
-                               uint4* spans, cudaStream_t s) {
+                               int M, const float* means3D, const float* shs, const float* colors_precomp,
+                               const float* opacities, const float* scales, const float* rotations, SplatRec* recs,
+                               int32_t* radii, uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids,
+                               uint32_t* min_keys, uint4* spans, cudaStream_t s) {
     if (N <= 0 || V <= 0) return 0;
     if (V > PP_MAXV) { gs_set_error("preprocess_multi: V=%d > %d", V, PP_MAXV); return 1; }
-    size_t smem = (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float);
+    if ((shs == nullptr) == (colors_precomp == nullptr)) { gs_set_error("preprocess_multi: exactly one of shs / colors_precomp"); return 1; }
+    size_t smem = shs ? (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float) : 0;
     if (smem > 48 * 1024)
         GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (N + PP_THREADS - 1) / PP_THREADS;
     preprocess_multi_kernel<<<blocks, PP_THREADS, smem, s>>>(views_dev, V, W, H, sh_degree, scale_modifier, N, M, means3D,
-                                                             shs, opacities, scales, rotations, recs, radii,
+                                                             shs, colors_precomp, opacities, scales, rotations, recs, radii,
                                                              tiles_touched, depth_keys, ids, min_keys, spans);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());

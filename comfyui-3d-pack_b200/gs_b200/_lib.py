@@ -73,7 +73,7 @@ lib.gs_b200_step_device_train.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_i
     [_P] * 5 + [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P, C.POINTER(C.c_int64), _P]
 lib.gs_b200_render_views.restype = C.c_int32
 lib.gs_b200_render_views.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_int32, C.c_int32] + \
-    [_P] * 5 + [_P, _P, C.POINTER(C.c_int64), _P]
+    [_P] * 6 + [_P, _P, C.POINTER(C.c_int64), _P]
 lib.gs_b200_step_host_dev_grads.restype = C.c_int32
 lib.gs_b200_step_host_dev_grads.argtypes = lib.gs_b200_step_host.argtypes
 lib.gs_b200_launch_count.restype = C.c_int64

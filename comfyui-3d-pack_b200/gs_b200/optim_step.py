@@ -183,9 +183,11 @@ def step_device_train(params: PackedParams, views: ViewSet, ref_images: torch.Te
     return int(pairs.value)
 
 
-def render_views(params: PackedParams, views: ViewSet, images: torch.Tensor = None, radii: torch.Tensor = None):
+def render_views(params: PackedParams, views: ViewSet, images: torch.Tensor = None, radii: torch.Tensor = None,
+                 colors_precomp: torch.Tensor = None):
     """Forward only over all views (gs_b200_render_views).  Returns (images[V,5,H,W], pair count); `radii`
-    (optional int32 [V,N]) receives the per-view radii (visibility filter = radii > 0)."""
+    (optional int32 [V,N]) receives the per-view radii (visibility filter = radii > 0).  colors_precomp [N,3]
+    replaces params.shs (LGM-style callers, Gen_3D_Modules/LGM/core/gs.py:75-84)."""
     import numpy as np
     assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
     if images is None:
@@ -196,7 +198,8 @@ def render_views(params: PackedParams, views: ViewSet, images: torch.Tensor = No
     pairs = C.c_int64(0)
     _lib.check(_lib.lib.gs_b200_render_views(
         views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
-        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), None if colors_precomp is not None else _ptr(params.shs),
+        None if colors_precomp is None else _ptr(colors_precomp.contiguous().float()), _ptr(params.opacities),
         _ptr(params.scales), _ptr(params.rotations), _ptr(images), None if radii is None else _ptr(radii),
         C.byref(pairs), _stream()))
     return images, int(pairs.value)

@@ -219,12 +219,13 @@ int32_t gs_b200_step_device_train(
 
 /* Forward only over V views that share the Gaussians (render nodes: orbit previews, LGM / TRELLIS style multi-view
  * renders — nodes.py:1130-1163, Gen_3D_Modules/LGM/core/gs.py:41-92): one pass over the parameters for all
- * views, then the per-view pipeline.  images: V x [5,H,W]; radii: optional V x [N] int32 (NULL = not kept). */
+ * views, then the per-view pipeline.  Exactly one of shs [N,M,3] / colors_precomp [N,3] (LGM passes colours,
+ * core/gs.py:75-84).  images: V x [5,H,W]; radii: optional V x [N] int32 (NULL = not kept). */
 int32_t gs_b200_render_views(
     int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
-    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* opacities,
-    const float* scales, const float* rotations, float* images, int32_t* radii, int64_t* num_rendered_out,
-    void* stream);
+    const float* views_dev, int32_t N, int32_t M, const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, const float* rotations, float* images, int32_t* radii,
+    int64_t* num_rendered_out, void* stream);
 
 /* ---- optimisation step around the rasterizer (GaussianModel, main_3DGS_renderer.py) -------------
  * Raw (pre-activation) parameters live in ONE packed buffer laid out like the gradient buffer:

@@ -298,6 +298,19 @@ def test_multiview_entries_chunking_and_empty_views(dev):
     rad = torch.empty(V, N, dtype=torch.int32, device=dev)
     optim_step.render_views(params, views, ic, rad)
     assert torch.equal(ia, ic) and int((rad[5] > 0).sum()) == 0 and int((rad[17] > 0).sum()) > 0
+    # LGM-style call: precomputed colours instead of SHs (Gen_3D_Modules/LGM/core/gs.py:75-84)
+    from gs_b200 import rasterizer as R
+    cols = torch.rand(N, 3, generator=torch.Generator().manual_seed(8)).to(dev)
+    id_, _ = optim_step.render_views(params, views, colors_precomp=cols)
+    for v in (0, 5, 11):
+        t = lambda a: torch.from_numpy(a).to(dev)
+        rs = R.GaussianRasterizationSettings(H, W, float(vnp[v, 38]), float(vnp[v, 39]), t(vnp[v, 35:38].copy()), 1.0,
+                                            t(vnp[v, :16].copy()).view(4, 4), t(vnp[v, 16:32].copy()).view(4, 4), deg,
+                                            t(vnp[v, 32:35].copy()), False, False)
+        with torch.no_grad():
+            col, _, dep, alp = R.GaussianRasterizer(rs)(means3D=cloud["means3D"], means2D=torch.zeros(N, 3, device=dev), colors_precomp=cols,
+                                                        opacities=cloud["opacities"], scales=cloud["scales"], rotations=cloud["rotations"])
+        assert torch.equal(col, id_[v, :3]) and torch.equal(dep, id_[v, 3:4]) and torch.equal(alp, id_[v, 4:5])
     seen = []
     def fn(v, img, out):
         seen.append(v); out.copy_(dl[v])
