@@ -14,6 +14,23 @@ from . import _lib
 _P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 
 
+_RNG = None
+
+
+def set_rng(generator=None):
+    """Reproducibility hook: with a CPU torch.Generator set, the three random draws of this module (occupancy-grid
+    update jitter, stratified sampling offsets, TV sample points) come from it (drawn on the CPU, moved to the device)
+    instead of the device RNG — this is how tests replay a CPU-generated reference run on the GPU.  None restores the default."""
+    global _RNG
+    _RNG = generator
+
+
+def _rand(shape, device):
+    if _RNG is None:
+        return torch.rand(shape, device=device, dtype=torch.float32)
+    return torch.rand(shape, generator=_RNG, dtype=torch.float32).to(device)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -102,7 +119,7 @@ class GridEncoder(nn.Module):
             raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
         dev = self.embeddings.device
         if inputs is None:
-            inputs = torch.rand(B, self.input_dim, device=dev) * 2 * bound - bound      # uniform in [-bound, bound]
+            inputs = _rand((B, self.input_dim), dev) * 2 * bound - bound               # uniform in [-bound, bound]
         x = _f32c(inputs.reshape(-1, self.input_dim))
         with torch.cuda.device(dev):
             _lib.check(_lib.lib.ngp_b200_grid_tv_grad(_P(x), x.shape[0], _P(_f32c(self.embeddings)), self._off_ptr, self.num_levels,
@@ -234,7 +251,7 @@ class OccGridEstimator(nn.Module):
                 occupied = occupied[torch.randint(len(occupied), (N,), device=dev)]
             indices = torch.cat([uniform, occupied], dim=0)
         coords = self.grid_coords[indices]
-        x = (coords + torch.rand_like(coords, dtype=torch.float32)) / R
+        x = (coords + _rand(tuple(coords.shape), coords.device)) / R
         lo, hi = self.aabbs[0, :3], self.aabbs[0, 3:]
         x = lo + x * (hi - lo)
         occ = occ_eval_fn(x).squeeze(-1)
@@ -249,7 +266,7 @@ class OccGridEstimator(nn.Module):
             raise NotImplementedError("cone_angle / t_min / t_max / alpha_fn are not used by the reference")
         ro = _f32c(rays_o); rd = _f32c(rays_d)
         n = ro.shape[0]
-        t_off = torch.rand(n, device=ro.device) * render_step_size if stratified else None
+        t_off = _rand((n,), ro.device) * render_step_size if stratified else None
         ray_indices, t_starts, t_ends = march_rays(ro, rd, self.binaries[0], self.aabbs[0], near_plane, far_plane,
                                                    render_step_size, t_off)
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and sigma_fn is not None and ray_indices.numel() > 0:

@@ -158,6 +158,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_training.npz"), **out)
     host_fixture(ns, captured)
     loop_fixture(ns)
+    ngp_fit_fixture()
     print("wrote ref_training.npz:", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 
 
@@ -268,6 +269,141 @@ def loop_fixture(ns):
         out["after_" + kname] = np.stack([sn[kname] for sn in snaps])
     np.savez_compressed(os.path.join(HERE, "ref_loop.npz"), **out)
     print("wrote ref_loop.npz: idx", out["idx"], "bg", out["step_bg"][:, 0], "max |dxyz|", float(np.abs(out["after_xyz"][-1] - out["init_xyz"]).max()))
+
+
+def ngp_fit_fixture():
+    """ref_ngp_fit.npz: InstantNGP.fit_nerf (MVs_Algorithms/NeRF/Instant_NGP.py:158-205) executed from the reference source
+    for two steps on the CPU (training mode: occupancy-grid update, stratified sampling, MSE losses, TV gradient, Adam with
+    the reference's learning rates), nerfacc / kiui served by oracle/ngp_oracle.py and drawing their random numbers from
+    the global CPU generator in the order the shims do (gs_b200/ngp.py::set_rng).  The hash tables are too large to store:
+    parameters are regenerated from the seed, the fixture keeps the MLP weights and a digest of the tables (values at a
+    fixed set of touched entries + sums).  tests/test_gpu_ngp.py replays it through the shims on the GPU."""
+    import sys, random as _random, tqdm as _tqdm
+    from torch import nn
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import gs_oracle as O, ngp_oracle as NO
+
+    class GridEncoder(nn.Module):
+        def __init__(self, num_levels=16):
+            super().__init__()
+            self.num_levels = num_levels
+            self.offsets = NO.grid_offsets(num_levels=num_levels)
+            self.embeddings = nn.Parameter(torch.zeros(int(self.offsets[-1]), 2))
+            self.output_dim = 2 * num_levels
+
+        def forward(self, xs, bound=1):
+            return NO.grid_encode(xs, self.embeddings, self.offsets, bound=float(bound), num_levels=self.num_levels)
+
+        @torch.no_grad()
+        def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
+            x = torch.rand(B, 3) * 2 * bound - bound
+            self.embeddings.grad += NO.grad_total_variation(x, self.embeddings.detach(), self.offsets, weight, bound=float(bound), num_levels=self.num_levels)
+
+    class MLP(nn.Module):
+        def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True):
+            super().__init__()
+            self.net = nn.ModuleList([nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=bias)
+                                      for l in range(num_layers)])
+
+        def forward(self, x):
+            for l, lin in enumerate(self.net):
+                x = lin(x)
+                if l != len(self.net) - 1:
+                    x = torch.relu(x)
+            return x
+
+    class OccGridEstimator(nn.Module):             # the estimator logic of gs_b200/ngp.py (nerfacc 0.5.3 semantics), marching by the oracle
+        def __init__(self, roi_aabb, resolution=64, levels=1):
+            super().__init__()
+            self.aabb = roi_aabb; R = self.R = resolution
+            self.occs = torch.zeros(R ** 3); self.binaries = torch.zeros(1, R, R, R, dtype=torch.bool)
+            g = torch.arange(R)
+            self.coords = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), dim=-1).reshape(-1, 3)
+
+        @torch.no_grad()
+        def update_every_n_steps(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16):
+            if step % n != 0:
+                return
+            assert step < warmup_steps
+            x = (self.coords + torch.rand(tuple(self.coords.shape), dtype=torch.float32)) / self.R
+            lo, hi = self.aabb[:3], self.aabb[3:]
+            x = lo + x * (hi - lo)
+            occ = occ_eval_fn(x).squeeze(-1)
+            self.occs = torch.maximum(self.occs * ema_decay, occ)
+            thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+            self.binaries = (self.occs > thre).view(self.binaries.shape)
+
+        @torch.no_grad()
+        def sampling(self, rays_o, rays_d, sigma_fn=None, near_plane=0.0, far_plane=1e10, render_step_size=1e-3, stratified=False, cone_angle=0.0):
+            n = rays_o.shape[0]
+            t_off = torch.rand((n,), dtype=torch.float32) * render_step_size if stratified else None
+            ri, t0, t1 = NO.march(rays_o, rays_d, self.binaries[0], self.aabb, near_plane, far_plane, render_step_size, t_off)
+            if sigma_fn is not None and ri.numel():
+                sig = sigma_fn(t0, t1, ri)
+                m = NO.visibility_mask(t0, t1, sig.detach(), ri, n, 1e-4, min(0.0, float(self.occs.mean())))
+                ri, t0, t1 = ri[m], t0[m], t1[m]
+            return ri, t0, t1
+    mods = {}
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; mods[name] = m; return m
+    nerfacc = mod("nerfacc", OccGridEstimator=OccGridEstimator,
+        render_weight_from_density=lambda t_starts, t_ends, sigmas, ray_indices=None, n_rays=None: NO.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices, n_rays),
+        accumulate_along_rays=lambda weights, values=None, ray_indices=None, n_rays=None: NO.accumulate_along_rays(weights, values, ray_indices, n_rays))
+    sn = lambda x, eps=1e-20: x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))
+    log = {"idx": []}
+
+    class _Rand:
+        def randint(self, a, b):
+            i = _random.randint(a, b); log["idx"].append(i); return i
+    img_src = open(os.path.join(REF, "shared_utils/image_utils.py")).read()
+    m = re.search(r"^def prepare_torch_img\(.*?(?=^def )", img_src, flags=re.S | re.M)
+    ins = {"torch": torch, "F": torch.nn.functional}
+    exec(m.group(0).replace('device="cuda"', 'device="cpu"'), ins)
+    comfy = types.SimpleNamespace(utils=types.SimpleNamespace(ProgressBar=lambda n: types.SimpleNamespace(update_absolute=lambda i: None)))
+    src = open(os.path.join(REF, "MVs_Algorithms/NeRF/Instant_NGP.py")).read()
+    body = src[src.index("class InstantNGP"):].replace("torch.cuda.synchronize()", "None")
+    body = body.replace("from kiui.gridencoder import GridEncoder", "pass")
+    mns = {"tqdm": _tqdm, "random": _Rand(), "np": np, "torch": torch, "nn": nn, "F": torch.nn.functional, "nerfacc": nerfacc, "comfy": comfy,
+           "SSIM": None, "MS_SSIM": None, "safe_normalize": sn, "orbit_camera": O.orbit_camera, "MLP": MLP, "trunc_exp": NO.trunc_exp,
+           "prepare_torch_img": ins["prepare_torch_img"], "GridEncoder": GridEncoder}
+    exec(compile(body, "ref_instant_ngp_cpu", "exec"), mns)
+    res, seed, K = 16, 777, 2
+    model = mns["InstantNGP"](resolution=res, device="cpu")
+    torch.manual_seed(seed); _random.seed(11)
+    for enc in (model.encoder_density, model.encoder):
+        enc.embeddings.data.uniform_(-0.5, 0.5)
+    for mlp in (model.mlp_density, model.mlp):
+        for lin in mlp.net:
+            lin.weight.data.uniform_(-0.4, 0.4)
+    init_d = model.encoder_density.embeddings.detach().clone(); init_c = model.encoder.embeddings.detach().clone()
+    n_ref = 2
+    ref_imgs = [torch.rand(res, res, 3) for _ in range(n_ref)]
+    ref_masks = [(torch.rand(res, res) > 0.4).float() for _ in range(n_ref)]
+    poses = [(1.75, -10.0 + 25.0 * i, 80.0 * i, 0.0, 0.0, 0.0) for i in range(n_ref)]
+    model.prepare_training(ref_imgs, ref_masks, poses, 49.1)
+    model.train()
+    model.fit_nerf(iters=K, bg_color=1)
+    out = {"seed": np.int64(seed), "res": np.int64(res), "K": np.int64(K), "idx": np.array(log["idx"], dtype=np.int64),
+           "levels": np.int64(model.encoder.num_levels), "poses": np.array(poses, dtype=np.float32),
+           "ref_imgs": torch.stack(ref_imgs).numpy(), "ref_masks": torch.stack(ref_masks).numpy()}
+    for name, mlp in (("mlp_density", model.mlp_density), ("mlp_color", model.mlp)):
+        for l, lin in enumerate(mlp.net):
+            out[f"{name}_w{l}"] = lin.weight.detach().numpy().copy()
+    g = torch.Generator().manual_seed(1)
+    for name, emb, init in (("emb_density", model.encoder_density.embeddings.detach(), init_d), ("emb_color", model.encoder.embeddings.detach(), init_c)):
+        changed = torch.nonzero((emb != init).any(dim=1))[:, 0]
+        pick = changed[torch.randperm(changed.numel(), generator=g)[:40000]]
+        rnd = torch.randint(0, emb.shape[0], (10000,), generator=g)
+        ids = torch.unique(torch.cat([pick, rnd]))
+        out[name + "_ids"] = ids.numpy(); out[name + "_vals"] = emb[ids].numpy().copy()
+        out[name + "_sum"] = np.float64(emb.double().sum()); out[name + "_abs_delta"] = np.float64((emb - init).double().abs().sum())
+        out[name + "_n_changed"] = np.int64(changed.numel())
+    out["binaries_count"] = np.int64(int(model.estimator.binaries.sum()))
+    np.savez_compressed(os.path.join(HERE, "ref_ngp_fit.npz"), **out)
+    print("wrote ref_ngp_fit.npz: idx", out["idx"], "changed entries", int(out["emb_density_n_changed"]), int(out["emb_color_n_changed"]),
+          "occupied cells", int(out["binaries_count"]))
+    for k in list(mods):
+        sys.modules.pop(k, None)
 
 
 def host_fixture(ns, captured):

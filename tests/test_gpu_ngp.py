@@ -190,3 +190,87 @@ def test_fused_mlp_matches_linear_stack(dev, din, dout, n):
     m2 = MLP(16, 2, 64, 3, bias=True).to(dev)
     assert m2(torch.randn(10, 16, device=dev)).shape == (10, 2)
     assert m(x.view(10, -1, din)).shape[-1] == dout if n % 10 == 0 else True
+
+
+@pytest.mark.skipif(__import__("os").environ.get("GS_B200_RUN_UNVERIFIED") != "1",
+                    reason="replay not yet confirmed on a B200 (GPU pod was draining); run with GS_B200_RUN_UNVERIFIED=1")
+def test_fit_nerf_steps_reproduce_the_reference_loop(dev):
+    """End to end for path B: InstantNGP.fit_nerf (Instant_NGP.py:158-205) was executed from the reference source for two
+    steps on the CPU with nerfacc / kiui served by the oracle (tests/golden/make_golden_training.py -> ref_ngp_fit.npz).
+    The same steps through the shims (CUDA hash-grid encode / scatter / TV, marcher, volume rendering, fused MLPs) with
+    the same random draws (gs_b200.ngp.set_rng) must land on the same parameters."""
+    import os, random
+    import nerfacc
+    from conftest import GOLDEN
+    from gs_b200 import ngp as NG
+    from kiui.gridencoder import GridEncoder
+    from kiui.nn import MLP, trunc_exp
+    F_ = np.load(os.path.join(GOLDEN, "ref_ngp_fit.npz"))
+    res, K, L = int(F_["res"]), int(F_["K"]), int(F_["levels"])
+    gen = torch.Generator()                                   # CPU generator = the fixture's global CPU stream
+    gen.manual_seed(int(F_["seed"]))
+    enc_d, enc_c = GridEncoder(num_levels=L).to(dev), GridEncoder(num_levels=L).to(dev)
+    init = []
+    for enc in (enc_d, enc_c):
+        e = torch.empty(enc.embeddings.shape).uniform_(-0.5, 0.5, generator=gen); init.append(e); enc.embeddings.data.copy_(e)
+    mlp_d, mlp_c = MLP(2 * L, 1, 32, 2, bias=False).to(dev), MLP(2 * L, 3, 32, 2, bias=False).to(dev)
+    for mlp in (mlp_d, mlp_c):
+        for lin in mlp.net:
+            lin.weight.data.copy_(torch.empty(lin.weight.shape).uniform_(-0.4, 0.4, generator=gen))
+    # the fixture drew the reference images / masks next from the same stream
+    n_ref = F_["ref_imgs"].shape[0]
+    ref_imgs = [torch.rand(res, res, 3, generator=gen) for _ in range(n_ref)]
+    ref_masks = [(torch.rand(res, res, generator=gen) > 0.4).float() for _ in range(n_ref)]
+    assert np.array_equal(torch.stack(ref_imgs).numpy(), F_["ref_imgs"]) and np.array_equal(torch.stack(ref_masks).numpy(), F_["ref_masks"])
+    img_gt = torch.stack(ref_imgs).permute(0, 3, 1, 2).contiguous().to(dev)       # prepare_torch_img at native size = identity resample
+    msk_gt = torch.stack(ref_masks).to(dev)
+    est = nerfacc.OccGridEstimator(roi_aabb=torch.tensor([-1.0, -1, -1, 1, 1, 1], device=dev), resolution=64, levels=1).to(dev)
+    est.train()
+    opt = torch.optim.Adam([{"params": enc_d.parameters(), "lr": 1e-2}, {"params": enc_c.parameters(), "lr": 1e-2},
+                            {"params": mlp_d.parameters(), "lr": 1e-3}, {"params": mlp_c.parameters(), "lr": 1e-3}])
+    density = lambda xs: trunc_exp(mlp_d(enc_d(xs)))
+    NG.set_rng(gen)
+    try:
+        for step in range(K):
+            i = int(F_["idx"][step])
+            radius, elev, azim, cx, cy, cz = [float(v) for v in F_["poses"][i]]
+            pose = O.orbit_camera(elev, azim, radius, target=np.array([cx, cy, cz], dtype=np.float32))
+            ro, rd = G.get_rays(pose, res, res, 49.1)
+            rog, rdg = ro.to(dev), rd.to(dev)
+            est.update_every_n_steps(step, occ_eval_fn=lambda xs: density(xs) * 5e-3, occ_thre=0.01, n=8)
+
+            def sigma_fn(t0, t1, ri):
+                return density(rog[ri] + rdg[ri] * (t0 + t1)[:, None] / 2.0).squeeze(-1)
+            with torch.no_grad():
+                ri, t0, t1 = est.sampling(rog, rdg, sigma_fn=sigma_fn, near_plane=0.01, far_plane=100, render_step_size=5e-3,
+                                          stratified=True, cone_angle=0)
+            xs = rog[ri] + rdg[ri] * (t0 + t1)[:, None] / 2.0
+            sig = density(xs).squeeze(-1); rgb = torch.sigmoid(mlp_c(enc_c(xs)))
+            w, _, _ = nerfacc.render_weight_from_density(t0, t1, sig, ray_indices=ri, n_rays=res * res)
+            color = nerfacc.accumulate_along_rays(w, values=rgb, ray_indices=ri, n_rays=res * res)
+            alpha = nerfacc.accumulate_along_rays(w, values=None, ray_indices=ri, n_rays=res * res)
+            color = color + (1.0 - alpha) * 1.0
+            image_pred = color.view(res, res, 3).clamp(0, 1).permute(2, 0, 1).contiguous()
+            alpha_pred = alpha.view(res, res).clamp(0, 1).contiguous()
+            loss = torch.nn.functional.mse_loss(image_pred, img_gt[i]) + 0.1 * torch.nn.functional.mse_loss(alpha_pred, msk_gt[i])
+            loss.backward()
+            enc_d.grad_total_variation(1e-8)
+            opt.step(); opt.zero_grad()
+    finally:
+        NG.set_rng(None)
+    # the occupancy threshold is the MEAN density of 262k jittered cells: a cell sitting on it may flip between CPU and GPU
+    assert abs(int(est.binaries.sum()) - int(F_["binaries_count"])) <= 0.005 * int(F_["binaries_count"])
+    for name, mlp in (("mlp_density", mlp_d), ("mlp_color", mlp_c)):
+        for l, lin in enumerate(mlp.net):
+            d = np.abs(lin.weight.detach().cpu().numpy() - F_[f"{name}_w{l}"])
+            assert float((d > 2e-4).mean()) <= 0.01 and float(d.max()) <= 2.0 * 1e-3 * K + 2e-4, (name, l, float(d.max()))
+    for name, enc, e0 in (("emb_density", enc_d, init[0]), ("emb_color", enc_c, init[1])):
+        emb = enc.embeddings.detach().cpu()
+        ids = torch.from_numpy(F_[name + "_ids"])
+        d = (emb[ids] - torch.from_numpy(F_[name + "_vals"])).abs().numpy()
+        # Adam (lr 1e-2) turns gradient signs into +-lr steps: entries whose only gradient is the 1e-8 TV term, or summation
+        # noise, can flip; everything else agrees to rounding
+        assert float((d > 2e-4).mean()) <= 0.01 and float(d.max()) <= 2.0 * 1e-2 * K + 2e-4, (name, float(d.max()), float((d > 2e-4).mean()))
+        n_changed = int((emb != e0).any(dim=1).sum())
+        assert abs(n_changed - int(F_[name + "_n_changed"])) <= 0.01 * int(F_[name + "_n_changed"])
+        assert abs(float(emb.double().sum()) - float(F_[name + "_sum"])) <= 1e-6 * emb.numel() * 0.5 + 2e-2 * 0.01 * n_changed
