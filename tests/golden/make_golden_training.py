@@ -472,6 +472,7 @@ def host_fixture(ns, captured):
     out["rays_pose"] = pose.numpy(); out["rays_o"] = ro.numpy(); out["rays_d"] = rd.numpy()
     ngp_fixture(out, O)
     mesh_fixture(out, O)
+    flexi_fixture(out, O)
     np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **out)
     print("wrote ref_host.npz:", sorted(out.keys()))
 
@@ -511,6 +512,47 @@ def mesh_fixture(out, O):
     out["mesh_pose"] = pose; out["mesh_proj"] = proj; out["mesh_hw"] = np.array([Hh, Ww]); out["mesh_albedo"] = albedo.numpy()
     for k in ("image", "alpha", "depth", "normal", "viewcos"):
         out["mesh_" + k] = res[k].numpy()
+    for k in list(mods):
+        sys.modules.pop(k, None)
+
+
+def flexi_fixture(out, O):
+    """FlexiCubesRenderer.get_orbit_camera + render_mesh (MVs_Algorithms/FlexiCubes/flexicubes_renderer.py:26-74, with
+    util.perspective / xfm_points / interpolate / SimpleMesh.auto_normals, FlexiCubes/util.py:25-93) executed from the
+    reference source for a BATCH of two views, `nvdiffrast.torch` served by oracle/dr_oracle.py: mask (antialiased),
+    normalised depth, per-face normals via the `arange(F)` attribute index trick, vertex normals, white background."""
+    import sys, importlib.util
+    from oracle import dr_oracle as DO
+    mods = {}
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; mods[name] = m; return m
+    nv = mod("nvdiffrast")
+    drt = mod("nvdiffrast.torch", RasterizeCudaContext=lambda *a, **k: object(), RasterizeGLContext=lambda *a, **k: object(),
+              rasterize=lambda ctx, pos, tri, resolution: DO.rasterize(pos, tri, tuple(resolution)),
+              interpolate=lambda attr, rast, tri, rast_db=None, diff_attrs=None: DO.interpolate(attr, rast, tri, rast_db=rast_db, diff_attrs=diff_attrs),
+              antialias=lambda color, rast, pos, tri: DO.antialias(color, rast, pos, tri))
+    nv.torch = drt
+    mod("kiui"); mod("kiui.cam", orbit_camera=O.orbit_camera)
+    usrc = open(os.path.join(REF, "MVs_Algorithms/FlexiCubes/util.py")).read()
+    util = types.ModuleType("FlexiCubes.util")
+    exec(compile(usrc, "ref_flexi_util", "exec"), util.__dict__)
+    fc = mod("FlexiCubes"); fc.util = util; sys.modules["FlexiCubes.util"] = util; mods["FlexiCubes.util"] = util
+    rsrc = open(os.path.join(REF, "MVs_Algorithms/FlexiCubes/flexicubes_renderer.py")).read().replace("device='cuda'", "device='cpu'").replace('device="cuda"', 'device="cpu"')
+    rns = {}
+    exec(compile(rsrc, "ref_flexi_renderer", "exec"), rns)
+    v, f, _ = DO.icosphere(2, 0.8)
+    mesh = util.SimpleMesh(v, f.long())
+    mesh.auto_normals()
+    mesh.v_nrm = util.safe_normalize(v)
+    R = rns["FlexiCubesRenderer"](True)
+    res = [40, 56]
+    cams = [R.get_orbit_camera(azimuth=az, elevation=el, fovy=45, iter_res=res, cam_radius=3.0, device="cpu") for az, el in ((30.0, 10.0), (200.0, -25.0))]
+    mv = torch.stack([c[0] for c in cams]).float(); mvp = torch.stack([c[1] for c in cams]).float()
+    with torch.no_grad():
+        outd = R.render_mesh(mesh, mv, mvp, res, return_types=["mask", "depth", "normal", "vertex_normal"], white_bg=True)
+    out["flexi_mv"] = mv.numpy(); out["flexi_mvp"] = mvp.numpy(); out["flexi_res"] = np.array(res)
+    for k, t in outd.items():
+        out["flexi_" + k] = t.numpy()
     for k in list(mods):
         sys.modules.pop(k, None)
 
