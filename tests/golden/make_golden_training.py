@@ -473,6 +473,7 @@ def host_fixture(ns, captured):
     ngp_fixture(out, O)
     mesh_fixture(out, O)
     flexi_fixture(out, O)
+    bake_fixture(out, O)
     np.savez_compressed(os.path.join(HERE, "ref_host.npz"), **out)
     print("wrote ref_host.npz:", sorted(out.keys()))
 
@@ -512,6 +513,38 @@ def mesh_fixture(out, O):
     out["mesh_pose"] = pose; out["mesh_proj"] = proj; out["mesh_hw"] = np.array([Hh, Ww]); out["mesh_albedo"] = albedo.numpy()
     for k in ("image", "alpha", "depth", "normal", "viewcos"):
         out["mesh_" + k] = res[k].numpy()
+    for k in list(mods):
+        sys.modules.pop(k, None)
+
+
+def bake_fixture(out, O):
+    """color_func_to_albedo (mesh_processer/mesh_utils.py:521-568) executed from the reference source: UV-space rasterize
+    (uv*2-1, z=0, w=1), interpolate positions and a coverage mask, query a colour function on the covered texels, pad.
+    `nvdiffrast.torch` = oracle/dr_oracle.py; `kiui.op.uv_padding` = this repo's shim (gs_b200/texops.py), so the pin is
+    on the composition, not on the padding rule (kiui is absent)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "comfyui-3d-pack_b200"))
+    from oracle import dr_oracle as DO
+    from gs_b200 import texops
+    mods = {}
+    def mod(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; mods[name] = m; return m
+    nv = mod("nvdiffrast")
+    drt = mod("nvdiffrast.torch", RasterizeCudaContext=lambda *a, **k: object(), RasterizeGLContext=lambda *a, **k: object(),
+              rasterize=lambda ctx, pos, tri, resolution: DO.rasterize(pos, tri, tuple(resolution)),
+              interpolate=lambda attr, rast, tri, rast_db=None, diff_attrs=None: DO.interpolate(attr, rast, tri, rast_db=rast_db, diff_attrs=diff_attrs))
+    nv.torch = drt
+    mod("kiui"); mod("kiui.op", uv_padding=texops.uv_padding)
+    mu = open(os.path.join(REF, "mesh_processer/mesh_utils.py")).read()
+    m = re.search(r"^def color_func_to_albedo\(.*?(?=^@torch|^def )", mu, flags=re.S | re.M)
+    fns = {"torch": torch, "np": np}
+    exec(m.group(0).replace('device="cuda"', 'device="cpu"'), fns)
+    v, f, uv = DO.icosphere(1, 0.5)
+    uv = uv * 0.8 + 0.1                                # keep the chart strictly inside the texture
+    mesh = types.SimpleNamespace(v=v, f=f, vt=uv, ft=f)
+    rgb_fn = lambda xyz: torch.stack([xyz[:, 0] + 0.5, xyz[:, 1] * xyz[:, 2] + 0.5, (xyz ** 2).sum(-1)], dim=1)
+    alb = fns["color_func_to_albedo"](mesh, rgb_fn, texture_resolution=48, padding=2, batch_size=1000, device="cpu", force_cuda_rast=True)
+    out["bake_albedo"] = alb.numpy(); out["bake_uv_scale"] = np.array([0.8, 0.1], dtype=np.float32)
     for k in list(mods):
         sys.modules.pop(k, None)
 
