@@ -272,11 +272,15 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
         unsigned long long* total = cv.take<unsigned long long>(1);
         uint32_t* min_key = (uint32_t*)cv.take<unsigned long long>(1);
         void* sort_scratch = cv.take<char>(sort_b);
-        GS_CUDA_CHECK(cudaMemsetAsync(min_key, 0xFF, 4, s));
         void* scan_scratch = cv.take<char>(scan_b);
-        { StageTimer t(0, s);
-        if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                 c.recs, radii, tiles, dkeys, ids, min_key, c.spans, s)) return 1; }
+        if (pre) {
+            min_key = pre->min_key;       // the multi-view pass has already written records, keys, tiles, spans and radii
+        } else {
+            GS_CUDA_CHECK(cudaMemsetAsync(min_key, 0xFF, 4, s));
+            StageTimer t(0, s);
+            if (gs_launch_preprocess(va, N, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                     c.recs, radii, tiles, dkeys, ids, min_key, c.spans, s)) return 1;
+        }
         STAGE_CHECK(c.dbg, s, "preprocess");
         int in_alt = 0;
         { StageTimer t(1, s);

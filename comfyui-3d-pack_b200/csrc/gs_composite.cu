@@ -1,0 +1,629 @@
+// Tile compositing, round-2 design: front-to-back alpha blend (forward) and its
+// back-to-front replay (backward).
+//
+// Replaces renderCUDA (forward.cu / backward.cu) of diff_gaussian_rasterization,
+// semantics per SURVEY.md App. A.1.6:  alpha = min(0.99, o*exp(power)); skip
+// power>0 or alpha<1/255; stop WITHOUT blending when T(1-alpha) < 1e-4;
+// color = C + T*bg, depth = sum(depth*alpha*T), alpha_out = sum(alpha*T).
+// Called where main_3DGS_renderer.py:927-936 calls the rasterizer and where
+// loss.backward() (main_3DGS.py:205) reaches its backward.
+//
+// Both kernels are instruction-issue bound (the 48 B splat records live in L2),
+// so the design minimises issued instructions per (pixel, splat) and takes the
+// record staging off the math warps:
+//  * one CTA per 16x16 tile = 4 math warps + 1 producer warp.  Math warp w owns
+//    the 8x8 quadrant (w&1, w>>1); every lane owns TWO pixels (x, y) and (x, y+4),
+//    so dx is shared and all per-pixel arithmetic is issued as packed f32x2
+//    (fma.rn.f32x2 / mul / add -> FFMA2 / FMUL2 / FADD2, scalar operands
+//    broadcast by the instruction itself);
+//  * the producer warp gathers the tile's records with one cp.async.bulk (TMA,
+//    UBLKCP) of 48 B per record into a ring of shared-memory stages; completion
+//    is tracked by an mbarrier per stage (expect_tx / complete_tx), math warps
+//    release a stage with one mbarrier.arrive per warp.  There is no
+//    __syncthreads() in the main loops;
+//  * each math warp decides by itself which records of a stage can reach
+//    alpha >= 1/255 inside its quadrant (exact minimum of the quadratic form over
+//    the 8x8 rectangle + slack): one test per lane and record, four ballots per
+//    128-record stage, then the warp walks only the set bits;
+//  * backward, per visit, only TWO values per pixel leave the lanes:
+//    G*dL/dalpha and alpha*T.  They are queued in shared memory ([pixel][slot])
+//    and, every 16 visits, a second phase with lanes = (slot, half-quadrant)
+//    turns them into the ten per-splat sums (six image moments of G*dL/dalpha in
+//    pixel-local coordinates, four colour/depth sums against per-pixel upstream
+//    gradients) with plain FFMAs and no cross-lane traffic beyond one final
+//    shfl.xor — the 12-SHFL transpose reduction per (warp, splat) of round 1 is
+//    gone.  One red.global.add per value and (quadrant, splat) leaves the CTA.
+#include "gs_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int NMATH = 4;                 // math warps per CTA
+constexpr int NTHREADS = (NMATH + 1) * 32;
+constexpr int BATCH = 128;               // records per ring stage
+constexpr uint32_t REC_BYTES = 48;
+constexpr uint32_t STAGE_BYTES = BATCH * REC_BYTES;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+
+// ---- packed f32x2 helpers (sm_100a: FFMA2 / FMUL2 / FADD2) ------------------------------------
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64 bc(float a) { return pk(a, a); }
+__device__ __forceinline__ float lo(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ---- mbarrier / bulk-copy helpers ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one record: global -> shared through the bulk-copy engine, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_s32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// May a splat reach alpha >= 1/255 somewhere in the 8x8 pixel square with corner (X0, Y0)?  Exact minimum of
+// q(u) = 0.5(A ux^2 + C uy^2) + B ux uy (log2 units) over the rectangle, with slack for fp32 rounding and the
+// approximate reciprocals; a rejected splat fails the per-pixel alpha test on every lane anyway.
+__device__ __forceinline__ bool quad_hit(const float4 g, const float4 c, float X0, float Y0) {
+    const float o = c.w;
+    if (!(o * 255.0f >= 1.0f) || __float_as_int(g.w) <= 0) return false;    // can never reach 1/255 (also NaN)
+    const float tau = lg2_approx(o * 255.0f) * 1.001f + 0.03f;
+    const float A = -2.0f * c.x, B = -c.y, C = -2.0f * c.z;
+    if (!(A > 0.f && A * C - B * B > 0.f)) return true;                     // not positive definite: per-pixel test decides
+    const float ux0 = X0 - g.x, ux1 = ux0 + 7.0f;
+    const float uy0 = Y0 - g.y, uy1 = uy0 + 7.0f;
+    const bool outx = (ux0 > 0.f) || (ux1 < 0.f);
+    const bool outy = (uy0 > 0.f) || (uy1 < 0.f);
+    float q = 0.f;
+    if (outx || outy) {
+        q = 3.0e38f;
+        if (outx) {
+            const float ue = (ux0 > 0.f) ? ux0 : ux1;
+            const float uy = fminf(fmaxf(-B * ue * rcp_approx(C), uy0), uy1);
+            q = 0.5f * (A * ue * ue + C * uy * uy) + B * ue * uy;
+        }
+        if (outy) {
+            const float ue = (uy0 > 0.f) ? uy0 : uy1;
+            const float ux = fminf(fmaxf(-B * ue * rcp_approx(A), ux0), ux1);
+            q = fminf(q, 0.5f * (A * ux * ux + C * ue * ue) + B * ux * ue);
+        }
+    }
+    return !(q > tau);      // NaN -> keep (conservative)
+}
+
+// hit masks of one stage for this warp's quadrant: bit l of m[i] <-> record i*32 + l
+__device__ __forceinline__ void stage_masks(uint32_t s_rec, int n, int lane, float X0, float Y0, uint32_t m[BATCH / 32]) {
+#pragma unroll
+    for (int i = 0; i < BATCH / 32; i++) {
+        const int j = i * 32 + lane;
+        bool hit = false;
+        if (j < n) {
+            const uint32_t ra = s_rec + j * REC_BYTES;
+            hit = quad_hit(lds128(ra), lds128(ra + 16), X0, Y0);
+        }
+        m[i] = __ballot_sync(0xFFFFFFFFu, hit);
+    }
+}
+
+// m[i] with i known only at run time, without putting the array into local memory
+__device__ __forceinline__ uint32_t pick_mask(const uint32_t m[BATCH / 32], int i) {
+    static_assert(BATCH == 128, "pick_mask is written for four groups");
+    return i == 0 ? m[0] : (i == 1 ? m[1] : (i == 2 ? m[2] : (i == 3 ? m[3] : 0u)));
+}
+
+// power (log2 units) of both pixels of the lane; the operation order is the scalar one of round 1
+// (t = cx*dx; t = fma(cy, dy, t); p = t*dx; p = fma(cz*dy, dy, p)) so forward and backward agree bit for bit.
+__device__ __forceinline__ u64 power2(const float4 c, float dx, u64 dy2) {
+    const float t = c.x * dx;
+    const u64 t2 = fma2(bc(c.y), dy2, bc(t));
+    const u64 p = mul2(t2, bc(dx));
+    const u64 q = mul2(bc(c.z), dy2);
+    return fma2(q, dy2, p);
+}
+
+struct RingState {
+    uint32_t stage = 0, phase = 0;
+    __device__ __forceinline__ void advance(int nstages) { if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1u; } }
+};
+
+// producer: ids (coalesced LDG) -> one 48 B bulk copy per record
+template <bool KEEP_IDS>
+__device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ list, int n,
+                                              uint32_t s_rec, uint32_t s_ids, uint32_t bar, int lane) {
+    uint32_t id[BATCH / 32];
+#pragma unroll
+    for (int i = 0; i < BATCH / 32; i++) {
+        const int j = i * 32 + lane;
+        id[i] = (j < n) ? __ldg(list + j) : 0u;
+    }
+    if (KEEP_IDS) {
+#pragma unroll
+        for (int i = 0; i < BATCH / 32; i++) {
+            const int j = i * 32 + lane;
+            if (j < n) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_ids + j * 4), "r"(id[i]) : "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * REC_BYTES);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < BATCH / 32; i++) {
+        const int j = i * 32 + lane;
+        if (j < n) bulk_g2s(s_rec + j * REC_BYTES, recs + id[i], REC_BYTES, bar);
+    }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS)
+composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
+                         const uint32_t* __restrict__ ranges, float* __restrict__ out_color,
+                         float* __restrict__ out_depth, float* __restrict__ out_alpha,
+                         uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
+    __shared__ __align__(128) unsigned char s_rec_raw[STAGES * STAGE_BYTES];
+    __shared__ __align__(8) u64 s_full[STAGES], s_empty[STAGES];
+    __shared__ uint32_t s_done, s_stop;
+    const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(s_rec_raw);
+    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(s_full), a_empty = (uint32_t)__cvta_generic_to_shared(s_empty);
+    const uint32_t a_done = (uint32_t)__cvta_generic_to_shared(&s_done), a_stop = (uint32_t)__cvta_generic_to_shared(&s_stop);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.y * va.tiles_x + blockIdx.x;
+    const uint32_t start = ranges[2 * tile], end = ranges[2 * tile + 1];
+    const int len = (int)(end - start);
+    const int nb = (len + BATCH - 1) / BATCH;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, NMATH); }
+        s_done = 0; s_stop = 0xFFFFFFFFu;
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NMATH) {
+        // ------------------------------ producer warp ------------------------------
+        RingState rs;
+        for (int b = 0; b < nb; b++) {
+            if (b >= STAGES) mbar_wait(a_empty + 8 * rs.stage, rs.phase ^ 1u);
+            const uint32_t done = __shfl_sync(0xFFFFFFFFu, ld_volatile_s32(a_done), 0);
+            if (done == NMATH) {         // every pixel of the tile has terminated: hand the math warps the stop batch
+                if (lane == 0) {
+                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_stop), "r"((uint32_t)b) : "memory");
+                    mbar_arrive(a_full + 8 * rs.stage);
+                }
+                break;
+            }
+            const int n = min(BATCH, len - b * BATCH);
+            produce_stage<false>(recs, point_list + start + b * BATCH, n, s_rec + rs.stage * STAGE_BYTES, 0u,
+                                 a_full + 8 * rs.stage, lane);
+            rs.advance(STAGES);
+        }
+        return;
+    }
+
+    // ------------------------------ math warps ------------------------------
+    const int X0 = blockIdx.x * GS_TILE + 8 * (warp & 1), Y0 = blockIdx.y * GS_TILE + 8 * (warp >> 1);
+    const int px = X0 + (lane & 7), pyA = Y0 + (lane >> 3), pyB = pyA + 4;
+    const bool inA = px < va.W && pyA < va.H, inB = px < va.W && pyB < va.H;
+    const float pxf = (float)px;
+    const float X0f = (float)X0, Y0f = (float)Y0;
+    // A pixel that has terminated (or lies outside the image) gets a NaN row coordinate: its power is then NaN, fails
+    // "power <= 0" and the pixel drops out of every later test without a per-pixel flag in the loop.
+    const float QNAN = __int_as_float(0x7fc00000);
+    float pyfA = inA ? (float)pyA : QNAN, pyfB = inB ? (float)pyB : QNAN;
+
+    float TA = 1.f, TB = 1.f;
+    u64 C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D2 = bc(0.f), A2 = bc(0.f);
+    uint32_t lastA = 0, lastB = 0;
+    bool warp_done = __all_sync(0xFFFFFFFFu, !inA && !inB);
+    if (warp_done && lane == 0) atomicAdd(&s_done, 1u);
+
+    RingState rs;
+    for (int b = 0; b < nb; b++) {
+        mbar_wait(a_full + 8 * rs.stage, rs.phase);
+        if ((uint32_t)b == ld_volatile_s32(a_stop)) break;
+        if (!warp_done) {
+            const int n = min(BATCH, len - b * BATCH);
+            const uint32_t sr = s_rec + rs.stage * STAGE_BYTES;
+            uint32_t m[BATCH / 32];
+            stage_masks(sr, n, lane, X0f, Y0f, m);
+            int i = -1;
+            uint32_t bal = 0, pos0 = 0, rg = 0;
+            for (;;) {
+                if (bal == 0) {          // next non-empty group of 32 records (the body below exists once in the code)
+                    if (i >= 0 && __all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
+                    do { ++i; bal = pick_mask(m, i); } while (bal == 0 && i < BATCH / 32);
+                    if (i >= BATCH / 32) break;
+                    pos0 = (uint32_t)(b * BATCH + i * 32 + 1);
+                    rg = sr + i * 32 * REC_BYTES;
+                }
+                const int jb = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const uint32_t ra = rg + jb * REC_BYTES;
+                const float4 g = lds128(ra), c = lds128(ra + 16);
+                const float dx = g.x - pxf;
+                const u64 dy2 = sub2(bc(g.y), pk(pyfA, pyfB));
+                const u64 p2 = power2(c, dx, dy2);
+                const float pA = lo(p2), pB = hi(p2);
+                const u64 a2 = mul2(bc(c.w), pk(ex2_approx(pA), ex2_approx(pB)));
+                const float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
+                const bool liveA = (pA <= 0.f) && !(alA < ALPHA_MIN);
+                const bool liveB = (pB <= 0.f) && !(alB < ALPHA_MIN);
+                if (!__any_sync(0xFFFFFFFFu, liveA || liveB)) continue;
+                const u64 al2 = pk(alA, alB), T2 = pk(TA, TB);
+                const u64 tt2 = mul2(T2, sub2(bc(1.f), al2));          // T * (1 - alpha)
+                const bool stopA = liveA && (lo(tt2) < 0.0001f), stopB = liveB && (hi(tt2) < 0.0001f);
+                const bool blA = liveA && !stopA, blB = liveB && !stopB;
+                const u64 w2raw = mul2(al2, T2);
+                const u64 w2 = pk(blA ? lo(w2raw) : 0.f, blB ? hi(w2raw) : 0.f);
+                const float4 k = lds128(ra + 32);
+                C0 = fma2(bc(k.x), w2, C0); C1 = fma2(bc(k.y), w2, C1); C2 = fma2(bc(k.z), w2, C2);
+                D2 = fma2(bc(g.z), w2, D2); A2 = add2(A2, w2);
+                TA = blA ? lo(tt2) : TA; TB = blB ? hi(tt2) : TB;
+                pyfA = stopA ? QNAN : pyfA; pyfB = stopB ? QNAN : pyfB;
+                lastA = blA ? pos0 + jb : lastA; lastB = blB ? pos0 + jb : lastB;
+            }
+            if (warp_done && lane == 0) atomicAdd(&s_done, 1u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty + 8 * rs.stage);
+        rs.advance(STAGES);
+    }
+    const u64 T2 = pk(TA, TB);
+
+    const size_t plane = (size_t)va.W * va.H;
+    const float bg0 = __ldg(va.bg), bg1 = __ldg(va.bg + 1), bg2 = __ldg(va.bg + 2);
+    if (inA) {
+        const size_t pix = (size_t)pyA * va.W + px;
+        const float T = lo(T2);
+        out_color[pix] = lo(C0) + T * bg0; out_color[plane + pix] = lo(C1) + T * bg1; out_color[2 * plane + pix] = lo(C2) + T * bg2;
+        out_depth[pix] = lo(D2); out_alpha[pix] = lo(A2); n_contrib[pix] = lastA; final_T[pix] = T;
+    }
+    if (inB) {
+        const size_t pix = (size_t)pyB * va.W + px;
+        const float T = hi(T2);
+        out_color[pix] = hi(C0) + T * bg0; out_color[plane + pix] = hi(C1) + T * bg1; out_color[2 * plane + pix] = hi(C2) + T * bg2;
+        out_depth[pix] = hi(D2); out_alpha[pix] = hi(A2); n_contrib[pix] = lastB; final_T[pix] = T;
+    }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+constexpr int SLOTS = 16;                          // queued visits per flush
+constexpr uint32_t QROW = (SLOTS + 1) * 8;         // bytes per pixel row of the queue: SLOTS float2 + 8 B pad (bank spread)
+constexpr uint32_t QWARP = 64 * QROW;              // queue bytes per math warp: 32 lane rows x {G dL/dalpha pair, alpha T pair}
+
+// Second phase of the backward: lanes = (slot, half of the lanes' pixel pairs).  Each lane sums, over its 16 pixel
+// pairs (pixel A = (x, y), pixel B = (x, y+4) of first-phase lane 8y+x), the queued (G*dL/dalpha, alpha*T) of its slot
+// against pixel-local coordinates and the per-pixel upstream gradients.
+__device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, uint32_t slot_base, int nq, int lane,
+                                         float Xc, float Yc, SplatGrad* __restrict__ sg) {
+    const int slot = lane & (SLOTS - 1), part = lane >> 4;
+    const uint32_t qg = q_base + slot * 8 + part * 16 * QROW, qd = qg + 32 * QROW;
+    const uint32_t ca = coef_base + part * 16 * 32;
+    float M0 = 0.f, M1 = 0.f, M2 = 0.f, My = 0.f, Mxy = 0.f, Myy = 0.f;
+    u64 Cr2 = bc(0.f), Cg2 = bc(0.f), Cb2 = bc(0.f), Cd2 = bc(0.f);       // (pixel A, pixel B) halves, added at the end
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        u64 s0 = bc(0.f), s1 = bc(0.f), s2 = bc(0.f);                       // row sums of w, w*LX, w*LX^2 for (row of A, row of B)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const int p = r * 8 + x;
+            u64 w, d, c0, c1, c2, cd;
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(qg + p * QROW));
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(d) : "r"(qd + p * QROW));
+            asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(ca + p * 32));
+            asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c2), "=l"(cd) : "r"(ca + p * 32 + 16));
+            const float LX = (float)x - 3.5f;
+            s0 = add2(s0, w); s1 = fma2(w, bc(LX), s1); s2 = fma2(w, bc(LX * LX), s2);
+            Cr2 = fma2(d, c0, Cr2); Cg2 = fma2(d, c1, Cg2); Cb2 = fma2(d, c2, Cb2); Cd2 = fma2(d, cd, Cd2);
+        }
+        const float LYA = (float)(part * 2 + r) - 3.5f, LYB = LYA + 4.0f;
+        const float a0 = lo(s0), b0 = hi(s0), a1 = lo(s1), b1 = hi(s1);
+        M0 += a0 + b0; M1 += a1 + b1; M2 += lo(s2) + hi(s2);
+        My = fmaf(a0, LYA, My); Mxy = fmaf(a1, LYA, Mxy); Myy = fmaf(a0, LYA * LYA, Myy);
+        My = fmaf(b0, LYB, My); Mxy = fmaf(b1, LYB, Mxy); Myy = fmaf(b0, LYB * LYB, Myy);
+    }
+    float Cr = lo(Cr2) + hi(Cr2), Cg = lo(Cg2) + hi(Cg2), Cb = lo(Cb2) + hi(Cb2), Cd = lo(Cd2) + hi(Cd2);
+#define XADD(v) v += __shfl_xor_sync(0xFFFFFFFFu, v, 16)
+    XADD(M0); XADD(M1); XADD(M2); XADD(My); XADD(Mxy); XADD(Myy); XADD(Cd); XADD(Cr); XADD(Cg); XADD(Cb);
+#undef XADD
+    if (slot < nq) {
+        const float4 si = lds128(slot_base + slot * 16);        // mean2D.x, mean2D.y, id, opacity
+        float* dst = reinterpret_cast<float*>(sg + __float_as_uint(si.z));
+        // pixel = centre + L, d = mean2D - pixel = u - L with u = mean2D - centre
+        const float u = si.x - Xc, v = si.y - Yc, o = si.w;
+        if (part == 0) {
+            atomicAdd(dst + 0, o * (u * M0 - M1));                                   // sum w dx
+            atomicAdd(dst + 1, o * (v * M0 - My));                                   // sum w dy
+            atomicAdd(dst + 2, Cd);                                                  // dL/ddepth
+            atomicAdd(dst + 4, o * (fmaf(u, fmaf(u, M0, -2.f * M1), M2)));           // sum w dx dx
+            atomicAdd(dst + 5, o * (fmaf(u, fmaf(v, M0, -My), fmaf(-v, M1, Mxy))));  // sum w dx dy
+        } else {
+            atomicAdd(dst + 6, o * (fmaf(v, fmaf(v, M0, -2.f * My), Myy)));          // sum w dy dy
+            atomicAdd(dst + 7, M0);                                                  // dL/dopacity (sum G dL/dalpha)
+            atomicAdd(dst + 8, Cr); atomicAdd(dst + 9, Cg); atomicAdd(dst + 10, Cb); // dL/drgb
+        }
+    }
+}
+
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
+composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
+                          const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
+                          const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
+                          const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
+                          SplatGrad* __restrict__ sg) {
+    // dynamic shared memory (> 48 KB): ring | queue | per-pixel upstream gradients | slot info | ids | barriers | wmax
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t s_q = s_rec + STAGES * STAGE_BYTES;
+    const uint32_t s_coef = s_q + NMATH * QWARP;
+    const uint32_t s_slot = s_coef + NMATH * 64 * 16;
+    const uint32_t s_ids = s_slot + NMATH * SLOTS * 16;
+    const uint32_t a_full = s_ids + STAGES * BATCH * 4, a_empty = a_full + 8 * STAGES;
+    volatile uint32_t* s_wmax = reinterpret_cast<volatile uint32_t*>(smem + (a_empty + 8 * STAGES - s_rec));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.y * va.tiles_x + blockIdx.x;
+    const uint32_t start = ranges[2 * tile], end = ranges[2 * tile + 1];
+    if (end <= start) return;
+
+    const int X0 = blockIdx.x * GS_TILE + 8 * (warp & 1), Y0 = blockIdx.y * GS_TILE + 8 * (warp >> 1);
+    const int px = X0 + (lane & 7), pyA = Y0 + (lane >> 3), pyB = pyA + 4;
+    const bool math = warp < NMATH;
+    const bool inA = math && px < va.W && pyA < va.H, inB = math && px < va.W && pyB < va.H;
+    const size_t plane = (size_t)va.W * va.H;
+    const size_t pixA = (size_t)pyA * va.W + px, pixB = (size_t)pyB * va.W + px;
+    const uint32_t lcA = inA ? n_contrib[pixA] : 0u, lcB = inB ? n_contrib[pixB] : 0u;
+    uint32_t wmax = max(lcA, lcB);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
+    if (math && lane == 0) s_wmax[warp] = wmax;
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, NMATH); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t nproc = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));   // list positions 1..nproc were blended
+    if (nproc == 0) return;
+    const int nb = (int)((nproc + BATCH - 1) / BATCH);
+
+    if (!math) {
+        // ------------------------------ producer warp: stages from the back of the list ------------------------------
+        RingState rs;
+        for (int it = 0; it < nb; it++) {
+            if (it >= STAGES) mbar_wait(a_empty + 8 * rs.stage, rs.phase ^ 1u);
+            const int base = (nb - 1 - it) * BATCH;
+            const int n = min(BATCH, (int)nproc - base);
+            produce_stage<true>(recs, point_list + start + base, n, s_rec + rs.stage * STAGE_BYTES,
+                                s_ids + rs.stage * BATCH * 4, a_full + 8 * rs.stage, lane);
+            rs.advance(STAGES);
+        }
+        return;
+    }
+
+    // ------------------------------ math warps ------------------------------
+    const float pxf = (float)px;
+    const u64 py2 = pk((float)pyA, (float)pyB);
+    const float X0f = (float)X0, Y0f = (float)Y0;
+    const float TfA = inA ? final_T[pixA] : 0.f, TfB = inB ? final_T[pixB] : 0.f;
+    float gC0A = 0.f, gC1A = 0.f, gC2A = 0.f, gDA = 0.f, gAA = 0.f, gC0B = 0.f, gC1B = 0.f, gC2B = 0.f, gDB = 0.f, gAB = 0.f;
+    if (inA) { gC0A = dL_dcolor[pixA]; gC1A = dL_dcolor[plane + pixA]; gC2A = dL_dcolor[2 * plane + pixA]; gDA = dL_ddepth[pixA]; gAA = dL_dalpha[pixA]; }
+    if (inB) { gC0B = dL_dcolor[pixB]; gC1B = dL_dcolor[plane + pixB]; gC2B = dL_dcolor[2 * plane + pixB]; gDB = dL_ddepth[pixB]; gAB = dL_dalpha[pixB]; }
+    const float bg0 = __ldg(va.bg), bg1 = __ldg(va.bg + 1), bg2 = __ldg(va.bg + 2);
+    const u64 gC0 = pk(gC0A, gC0B), gC1 = pk(gC1A, gC1B), gC2 = pk(gC2A, gC2B), gD = pk(gDA, gDB), gA = pk(gAA, gAB);
+    const u64 bgT = pk(-TfA * (bg0 * gC0A + bg1 * gC1A + bg2 * gC2A), -TfB * (bg0 * gC0B + bg1 * gC1B + bg2 * gC2B));
+
+    const uint32_t q_base = s_q + warp * QWARP;
+    const uint32_t coef_base = s_coef + warp * 64 * 16;
+    const uint32_t slot_base = s_slot + warp * SLOTS * 16;
+    sts128(coef_base + lane * 32, make_float4(gC0A, gC0B, gC1A, gC1B));           // (A, B) pairs per channel: the
+    sts128(coef_base + lane * 32 + 16, make_float4(gC2A, gC2B, gDA, gDB));         // second phase multiplies them packed
+    const uint32_t qwG = q_base + lane * QROW, qwD = qwG + 32 * QROW;     // this lane's rows of the two queue arrays
+    const float Xc = X0f + 3.5f, Yc = Y0f + 3.5f;
+    __syncwarp();
+
+    u64 T2 = pk(TfA, TfB);
+    // Upstream gradients are per-pixel constants and the blend is linear in the channels, so the five "colour behind
+    // this splat" recurrences of the package collapse into ONE on the projected scalar s_j = gC.rgb_j + gD*depth_j + gA:
+    // dL/dalpha_j = T_j * (s_j - behind_j) + bg term.
+    u64 behind = bc(0.f);
+    int nq = 0;
+
+    RingState rs;
+    for (int it = 0; it < nb; it++) {
+        mbar_wait(a_full + 8 * rs.stage, rs.phase);
+        const int base = (nb - 1 - it) * BATCH;
+        if ((uint32_t)base < wmax) {                      // otherwise the whole stage is past this warp's last contributor
+            const int n = min(BATCH, (int)nproc - base);
+            const uint32_t sr = s_rec + rs.stage * STAGE_BYTES;
+            const uint32_t si = s_ids + rs.stage * BATCH * 4;
+            uint32_t m[BATCH / 32];
+            stage_masks(sr, n, lane, X0f, Y0f, m);
+            int i = BATCH / 32;
+            uint32_t bal = 0, rg = 0, ig = 0, pos0 = 0;
+            for (;;) {
+                if (bal == 0) {          // next non-empty group of 32 records, from the back
+                    do { --i; bal = pick_mask(m, i); } while (bal == 0 && i >= 0);
+                    if (i < 0) break;
+                    rg = sr + i * 32 * REC_BYTES; ig = si + i * 32 * 4; pos0 = (uint32_t)(base + i * 32);
+                }
+                const int jb = 31 - __clz(bal);
+                bal &= ~(1u << jb);
+                const uint32_t ra = rg + jb * REC_BYTES;
+                const float4 g = lds128(ra), c = lds128(ra + 16);
+                const float dx = g.x - pxf;
+                const u64 dy2 = sub2(bc(g.y), py2);
+                const u64 p2 = power2(c, dx, dy2);
+                const float pA = lo(p2), pB = hi(p2);
+                float GA = ex2_approx(pA), GB = ex2_approx(pB);
+                const u64 a2 = mul2(bc(c.w), pk(GA, GB));
+                float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
+                const uint32_t pos = pos0 + jb;
+                const bool actA = (pos < lcA) && (pA <= 0.f) && !(alA < ALPHA_MIN);
+                const bool actB = (pos < lcB) && (pB <= 0.f) && !(alB < ALPHA_MIN);
+                if (!__any_sync(0xFFFFFFFFu, actA || actB)) continue;
+                // a pixel the splat was not blended into runs the same code with alpha = G = 0: T, behind and both
+                // outputs are then unchanged / zero (the pending term of the previous splat is still applied once)
+                alA = actA ? alA : 0.f; alB = actB ? alB : 0.f;
+                GA = actA ? GA : 0.f; GB = actB ? GB : 0.f;
+                const u64 al2 = pk(alA, alB);
+                const float4 k = lds128(ra + 32);
+                const u64 om = sub2(bc(1.f), al2);
+                const u64 ria = pk(rcp_approx(lo(om)), rcp_approx(hi(om)));   // alpha = 0 -> rcp(1) = 1 exactly
+                T2 = mul2(T2, ria);                                   // T_j = T_{j+1} / (1 - alpha_j)
+                const u64 dchan = mul2(al2, T2);                      // d pixel / d channel_j = alpha_j T_j
+                u64 sj = fma2(bc(k.x), gC0, gA);
+                sj = fma2(bc(k.y), gC1, sj);
+                sj = fma2(bc(k.z), gC2, sj);
+                sj = fma2(bc(g.z), gD, sj);
+                const u64 ds = sub2(sj, behind);                      // s_j - (colour behind splat j)
+                const u64 dL_da = fma2(ds, T2, mul2(bgT, ria));       // *T_j, + (-T_final/(1-alpha)) * bg.dL_dpixel
+                behind = fma2(al2, ds, behind);                       // colour behind splat j-1
+                // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6)
+                const u64 gda = mul2(pk(GA, GB), dL_da);              // G * dL/dalpha; w = opacity * gda is applied per slot
+                const uint32_t qo = (uint32_t)nq * 8;
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(qwG + qo), "l"(gda) : "memory");
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(qwD + qo), "l"(dchan) : "memory");
+                if (lane == 0) {
+                    const uint32_t sa = slot_base + nq * 16;
+                    sts64(sa, g.x, g.y);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 8), "r"(ld_volatile_s32(ig + jb * 4)) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(c.w) : "memory");
+                }
+                if (++nq == SLOTS) {
+                    __syncwarp();
+                    flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg);
+                    __syncwarp();
+                    nq = 0;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty + 8 * rs.stage);
+        rs.advance(STAGES);
+    }
+    if (nq > 0) {
+        __syncwarp();
+        flush_queue(q_base, coef_base, slot_base, nq, lane, Xc, Yc, sg);
+    }
+}
+
+constexpr size_t bwd_smem_bytes(int stages) {
+    return (size_t)stages * STAGE_BYTES + NMATH * QWARP + NMATH * 64 * 16 + NMATH * SLOTS * 16 + (size_t)stages * BATCH * 4 +
+           16 * (size_t)stages + 16;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+// round-1 kernels (gs_render.cu), kept selectable for A/B measurements: GS_B200_COMPOSITE=r1
+int gs_launch_render_forward_r1(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+                                const uint32_t* ranges, float* out_color, float* out_depth, float* out_alpha,
+                                uint32_t* n_contrib, float* final_T, cudaStream_t s);
+int gs_launch_render_backward_r1(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+                                 const uint32_t* ranges, const uint32_t* n_contrib, const float* final_T,
+                                 const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                                 SplatGrad* sg, cudaStream_t s);
+
+#include <atomic>
+static std::atomic<int> g_composite_mode{[]() { const char* e = getenv("GS_B200_COMPOSITE"); return (e && e[0] == 'r') ? 1 : 0; }()};
+static bool use_r1() { return g_composite_mode.load(std::memory_order_relaxed) == 1; }
+extern "C" int32_t gs_b200_debug_set_composite(int32_t mode) {
+    if (mode != 0 && mode != 1) { gs_set_error("composite mode must be 0 (round-2 kernels) or 1 (round-1 kernels)"); return 1; }
+    g_composite_mode.store(mode);
+    return 0;
+}
+
+int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+                             const uint32_t* ranges, float* out_color, float* out_depth, float* out_alpha,
+                             uint32_t* n_contrib, float* final_T, cudaStream_t s) {
+    if (use_r1()) return gs_launch_render_forward_r1(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T, s);
+    dim3 grid(va.tiles_x, va.tiles_y);
+    static const int stages = env_int("GS_B200_FWD_STAGES", 3);
+    if (stages == 2)
+        composite_forward_kernel<2><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+    else if (stages == 4)
+        composite_forward_kernel<4><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+    else
+        composite_forward_kernel<3><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+    gs_count_launches(1);
+    GS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+                              const uint32_t* ranges, const uint32_t* n_contrib, const float* final_T,
+                              const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                              SplatGrad* sg, cudaStream_t s) {
+    if (use_r1()) return gs_launch_render_backward_r1(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s);
+    dim3 grid(va.tiles_x, va.tiles_y);
+    static const int stages = env_int("GS_B200_BWD_STAGES", 2);
+    static const int occ = env_int("GS_B200_BWD_OCC", 4);
+#define BWD(ST, OC)                                                                                                        \
+    do {                                                                                                                   \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, OC>,                            \
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST)); \
+        GS_CUDA_CHECK(attr);                                                                                               \
+        composite_backward_kernel<ST, OC><<<grid, NTHREADS, bwd_smem_bytes(ST), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+    } while (0)
+    if (stages == 3) { if (occ >= 4) BWD(3, 4); else BWD(3, 3); }
+    else             { if (occ >= 5) BWD(2, 5); else if (occ == 3) BWD(2, 3); else BWD(2, 4); }
+#undef BWD
+    gs_count_launches(1);
+    GS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}

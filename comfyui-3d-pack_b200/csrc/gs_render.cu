@@ -302,7 +302,7 @@ render_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uin
 
 }  // namespace
 
-int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+int gs_launch_render_forward_r1(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
                              const uint32_t* ranges, float* out_color, float* out_depth, float* out_alpha,
                              uint32_t* n_contrib, float* final_T, cudaStream_t s) {
     dim3 grid(va.tiles_x, va.tiles_y);
@@ -313,7 +313,7 @@ int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uin
     return 0;
 }
 
-int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
+int gs_launch_render_backward_r1(const ViewArgs& va, const SplatRec* recs, const uint32_t* point_list,
                               const uint32_t* ranges, const uint32_t* n_contrib, const float* final_T,
                               const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                               SplatGrad* sg, cudaStream_t s) {

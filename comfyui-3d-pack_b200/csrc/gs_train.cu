@@ -92,10 +92,13 @@ adam_sh_kernel(size_t n4, int row, AdamArgs a, const float4* __restrict__ g, flo
     const int c0 = (int)((i * 4) % (size_t)row);
     float4 pv = p[i], mv = m1[i], vv = m2[i];
     const float4 gv = g[i];
-    adam_one(pv.x, mv.x, vv.x, a.grad_scale * gv.x, c0 + 0 < 3 ? a.lr_dc : a.lr_rest, a);
-    adam_one(pv.y, mv.y, vv.y, a.grad_scale * gv.y, c0 + 1 < 3 ? a.lr_dc : a.lr_rest, a);
-    adam_one(pv.z, mv.z, vv.z, a.grad_scale * gv.z, c0 + 2 < 3 ? a.lr_dc : a.lr_rest, a);
-    adam_one(pv.w, mv.w, vv.w, a.grad_scale * gv.w, c0 + 3 < 3 ? a.lr_dc : a.lr_rest, a);
+    // a float4 may straddle a row boundary when row = 3M is not a multiple of 4 (sh_degree 0 and 2): the wrapped
+    // elements are the NEXT Gaussian's dc coefficients
+    auto lr_of = [&](int k) { int c = c0 + k; if (c >= row) c -= row; return c < 3 ? a.lr_dc : a.lr_rest; };
+    adam_one(pv.x, mv.x, vv.x, a.grad_scale * gv.x, lr_of(0), a);
+    adam_one(pv.y, mv.y, vv.y, a.grad_scale * gv.y, lr_of(1), a);
+    adam_one(pv.z, mv.z, vv.z, a.grad_scale * gv.z, lr_of(2), a);
+    adam_one(pv.w, mv.w, vv.w, a.grad_scale * gv.w, lr_of(3), a);
     p[i] = pv; m1[i] = mv; m2[i] = vv;
 }
 

@@ -172,6 +172,10 @@ class GaussianTrainer:
         s = self.step_count - 1
         if p.density_start_iter <= s <= p.density_end_iter:
             # NOTE: radii of the LAST view of the batch, as the reference (main_3DGS.py:211) — here also the summed means2D grad
+            if world > 1:
+                # the all-reduced buffer is world x the global-mean gradient (per-view loss scale world/total); Adam
+                # compensates with grad_scale, the densification statistics must too or the threshold shrinks by 1/world
+                self.g_means2D.mul_(1.0 / world)
             _lib.check(_lib.lib.gs_b200_densify_stats(self.N, _ptr(self.g_means2D), _ptr(self.radii), _ptr(self.grad_accum),
                                                       _ptr(self.denom), _ptr(self.max_radii2D), _stream()))
             if s % p.densification_interval == 0:

@@ -92,6 +92,12 @@ const char* gs_b200_last_error(void);
 int32_t gs_b200_set_tile_culling(int32_t mode);
 int32_t gs_b200_get_tile_culling(void);
 
+/* Measurement switch (no reference counterpart): which tile-composite kernels run.  0 (default): the round-2
+ * kernels (gs_composite.cu: two pixels per lane in packed f32x2, TMA-fed mbarrier ring, queued gradient phase);
+ * 1: the round-1 kernels (gs_render.cu), kept for A/B timing.  Results agree (images bit for bit).
+ * Initial value from the environment variable GS_B200_COMPOSITE ("r1" selects 1). */
+int32_t gs_b200_debug_set_composite(int32_t mode);
+
 /* Forward — replaces `_C.rasterize_gaussians` as called from
  * GaussianRasterizer.forward (main_3DGS_renderer.py:927-936).
  *   M        number of SH coefficients per channel in `shs` ([N,M,3]); ignored when colors_precomp != NULL

@@ -32,10 +32,13 @@ def test_activate_matches_reference_activations(dev):
     assert torch.allclose(r, torch.nn.functional.normalize(rr), atol=1e-6)
 
 
-def test_fused_adam_matches_torch_adam_through_activations(dev):
-    """training_setup (main_3DGS_renderer.py:435-453): six groups, eps=1e-15; gradients arrive wrt ACTIVATED values."""
+@pytest.mark.parametrize("M", [1, 4, 9])
+def test_fused_adam_matches_torch_adam_through_activations(dev, M):
+    """training_setup (main_3DGS_renderer.py:435-453): six groups, eps=1e-15; gradients arrive wrt ACTIVATED values.
+    M = 1 and 9 (rows of 3 and 27 floats) make the 128-bit SH pass straddle Gaussian rows: the dc / rest learning rates
+    must follow the coefficient, not the position inside the float4."""
     from gs_b200 import _lib
-    N, M = 3000, 4
+    N = 3000
     g = torch.Generator(device="cpu").manual_seed(1)
     sizes = [3 * N, 3 * M * N, N, 3 * N, 4 * N]
     raw = torch.randn(sum(sizes), generator=g).to(dev) * 0.5
