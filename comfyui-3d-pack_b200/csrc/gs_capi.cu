@@ -498,6 +498,8 @@ struct StepCache {
     }
 };
 thread_local StepCache g_step;
+struct UserSink { gs_b200_grad_sink fn = nullptr; void* user = nullptr; int nchunks = 1; };
+thread_local UserSink g_user_sink;
 
 struct PackedPtrs { float *means, *shs, *opac, *scales, *rots, *m2d; float* colors = nullptr; /* [N,3] instead of shs: forward-only */ };
 PackedPtrs carve_packed(float* base, size_t N, size_t M, bool with_m2d) {
@@ -530,6 +532,16 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     const StepOpts defaults;
     const StepOpts& O = opts ? *opts : defaults;
     if (C.ensure_init()) return 1;
+    GradSink user_sink;
+    if (!sink && g_user_sink.fn && !O.forward_only) {      // data-parallel caller: all-reduce chunks behind the last pass
+        user_sink.ctx = &g_user_sink;
+        user_sink.nchunks = g_user_sink.nchunks;
+        user_sink.fn = [](void* vp, int first, int count, cudaStream_t st) {
+            UserSink* u = (UserSink*)vp;
+            u->fn(u->user, first, count, (void*)st);
+        };
+        sink = &user_sink;
+    }
     const size_t npix = (size_t)H * W;
     // View chunks: one batched preprocess / preprocess-backward pass per chunk of <= 16 views, on the aux stream:
     //   aux stream:   pre(0) | pre(1) ............ bwd(0) | pre(2) ....... bwd(1) | ... | bwd(last)
@@ -733,6 +745,12 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     return 0;
 }
 }  // namespace
+
+int32_t gs_b200_set_grad_sink(gs_b200_grad_sink sink, void* user, int32_t nchunks) {
+    if (sink && (nchunks < 1 || nchunks > 64)) { gs_set_error("set_grad_sink: nchunks must be 1..64"); return 1; }
+    g_user_sink.fn = sink; g_user_sink.user = user; g_user_sink.nchunks = sink ? nchunks : 1;
+    return 0;
+}
 
 int32_t gs_b200_step_device(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier,
                             const float* views_host, const float* views_dev, int32_t N, int32_t M,

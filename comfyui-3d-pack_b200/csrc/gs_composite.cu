@@ -92,10 +92,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");   // suspend-time hint (ns): sleep in hardware, do not poll
 }
 // one record: global -> shared through the bulk-copy engine, completion counted on `bar`
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -200,6 +200,43 @@ __device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs,
     }
 }
 
+// ---- one visit of the forward, split into a state-free front half and the sequential blend ------------------------
+struct FwdFront { u64 al2; float4 g; bool liveA, liveB; };
+
+__device__ __forceinline__ FwdFront fwd_front(uint32_t ra, float pxf, float pyfA, float pyfB) {
+    FwdFront f;
+    f.g = lds128(ra);
+    const float4 c = lds128(ra + 16);
+    const float dx = f.g.x - pxf;
+    const u64 dy2 = sub2(bc(f.g.y), pk(pyfA, pyfB));
+    const u64 p2 = power2(c, dx, dy2);
+    const float pA = lo(p2), pB = hi(p2);
+    const u64 a2 = mul2(bc(c.w), pk(ex2_approx(pA), ex2_approx(pB)));
+    const float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
+    f.al2 = pk(alA, alB);
+    f.liveA = (pA <= 0.f) && !(alA < ALPHA_MIN);       // a terminated pixel has a NaN power
+    f.liveB = (pB <= 0.f) && !(alB < ALPHA_MIN);
+    return f;
+}
+
+__device__ __forceinline__ void fwd_back(const FwdFront& f, bool liveA, bool liveB, uint32_t ra, uint32_t pos, float& TA,
+                                         float& TB, u64& C0, u64& C1, u64& C2, u64& D2, u64& A2, uint32_t& lastA, uint32_t& lastB,
+                                         float& pyfA, float& pyfB) {
+    const u64 T2 = pk(TA, TB);
+    const u64 tt2 = mul2(T2, sub2(bc(1.f), f.al2));          // T * (1 - alpha)
+    const bool stopA = liveA && (lo(tt2) < 0.0001f), stopB = liveB && (hi(tt2) < 0.0001f);
+    const bool blA = liveA && !stopA, blB = liveB && !stopB;
+    const u64 w2raw = mul2(f.al2, T2);
+    const u64 w2 = pk(blA ? lo(w2raw) : 0.f, blB ? hi(w2raw) : 0.f);
+    const float4 k = lds128(ra + 32);
+    C0 = fma2(bc(k.x), w2, C0); C1 = fma2(bc(k.y), w2, C1); C2 = fma2(bc(k.z), w2, C2);
+    D2 = fma2(bc(f.g.z), w2, D2); A2 = add2(A2, w2);
+    TA = blA ? lo(tt2) : TA; TB = blB ? hi(tt2) : TB;
+    lastA = blA ? pos : lastA; lastB = blB ? pos : lastB;
+    const float QNAN = __int_as_float(0x7fc00000);           // terminated: the pixel's row coordinate becomes NaN
+    pyfA = stopA ? QNAN : pyfA; pyfB = stopB ? QNAN : pyfB;
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -275,41 +312,31 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
             const uint32_t sr = s_rec + rs.stage * STAGE_BYTES;
             uint32_t m[BATCH / 32];
             stage_masks(sr, n, lane, X0f, Y0f, m);
-            int i = -1;
-            uint32_t bal = 0, pos0 = 0, rg = 0;
-            for (;;) {
-                if (bal == 0) {          // next non-empty group of 32 records (the body below exists once in the code)
-                    if (i >= 0 && __all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
-                    do { ++i; bal = pick_mask(m, i); } while (bal == 0 && i < BATCH / 32);
-                    if (i >= BATCH / 32) break;
-                    pos0 = (uint32_t)(b * BATCH + i * 32 + 1);
-                    rg = sr + i * 32 * REC_BYTES;
+#pragma unroll
+            for (int i = 0; i < BATCH / 32; i++) {
+                uint32_t bal = m[i];
+                const uint32_t rg = sr + i * 32 * REC_BYTES;
+                const uint32_t pos0 = (uint32_t)(b * BATCH + i * 32 + 1);
+                // two visits per iteration: their front halves (load, power, exp, alpha) are independent and interleave;
+                // the blend updates run in list order
+                while (bal) {
+                    const int j0 = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const bool two = bal != 0;
+                    const int j1 = two ? __ffs(bal) - 1 : j0;
+                    bal &= bal - 1;
+                    FwdFront f0 = fwd_front(rg + j0 * REC_BYTES, pxf, pyfA, pyfB);
+                    FwdFront f1 = fwd_front(rg + j1 * REC_BYTES, pxf, pyfA, pyfB);
+                    if (__any_sync(0xFFFFFFFFu, f0.liveA || f0.liveB))
+                        fwd_back(f0, f0.liveA, f0.liveB, rg + j0 * REC_BYTES, pos0 + j0, TA, TB, C0, C1, C2, D2, A2, lastA, lastB, pyfA, pyfB);
+                    if (two) {
+                        // visit 1's front half saw the row coordinates from before visit 0: drop pixels that just terminated
+                        const bool l1A = f1.liveA && (pyfA == pyfA), l1B = f1.liveB && (pyfB == pyfB);
+                        if (__any_sync(0xFFFFFFFFu, l1A || l1B))
+                            fwd_back(f1, l1A, l1B, rg + j1 * REC_BYTES, pos0 + j1, TA, TB, C0, C1, C2, D2, A2, lastA, lastB, pyfA, pyfB);
+                    }
                 }
-                const int jb = __ffs(bal) - 1;
-                bal &= bal - 1;
-                const uint32_t ra = rg + jb * REC_BYTES;
-                const float4 g = lds128(ra), c = lds128(ra + 16);
-                const float dx = g.x - pxf;
-                const u64 dy2 = sub2(bc(g.y), pk(pyfA, pyfB));
-                const u64 p2 = power2(c, dx, dy2);
-                const float pA = lo(p2), pB = hi(p2);
-                const u64 a2 = mul2(bc(c.w), pk(ex2_approx(pA), ex2_approx(pB)));
-                const float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
-                const bool liveA = (pA <= 0.f) && !(alA < ALPHA_MIN);
-                const bool liveB = (pB <= 0.f) && !(alB < ALPHA_MIN);
-                if (!__any_sync(0xFFFFFFFFu, liveA || liveB)) continue;
-                const u64 al2 = pk(alA, alB), T2 = pk(TA, TB);
-                const u64 tt2 = mul2(T2, sub2(bc(1.f), al2));          // T * (1 - alpha)
-                const bool stopA = liveA && (lo(tt2) < 0.0001f), stopB = liveB && (hi(tt2) < 0.0001f);
-                const bool blA = liveA && !stopA, blB = liveB && !stopB;
-                const u64 w2raw = mul2(al2, T2);
-                const u64 w2 = pk(blA ? lo(w2raw) : 0.f, blB ? hi(w2raw) : 0.f);
-                const float4 k = lds128(ra + 32);
-                C0 = fma2(bc(k.x), w2, C0); C1 = fma2(bc(k.y), w2, C1); C2 = fma2(bc(k.z), w2, C2);
-                D2 = fma2(bc(g.z), w2, D2); A2 = add2(A2, w2);
-                TA = blA ? lo(tt2) : TA; TB = blB ? hi(tt2) : TB;
-                pyfA = stopA ? QNAN : pyfA; pyfB = stopB ? QNAN : pyfB;
-                lastA = blA ? pos0 + jb : lastA; lastB = blB ? pos0 + jb : lastB;
+                if (__all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
             }
             if (warp_done && lane == 0) atomicAdd(&s_done, 1u);
         }
@@ -394,6 +421,57 @@ __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, ui
             atomicAdd(dst + 8, Cr); atomicAdd(dst + 9, Cg); atomicAdd(dst + 10, Cb); // dL/drgb
         }
     }
+}
+
+// ---- one visit of the backward: recurrence-free front half, then the short sequential part ---------------------------
+struct BwdFront { u64 al2, G2, ria, sj, bgr; float gx, gy, o; bool any; };
+
+__device__ __forceinline__ BwdFront bwd_front(uint32_t ra, uint32_t pos, float pxf, u64 py2, uint32_t lcA, uint32_t lcB, u64 gC0,
+                                              u64 gC1, u64 gC2, u64 gD, u64 gA, u64 bgT) {
+    BwdFront f;
+    const float4 g = lds128(ra), c = lds128(ra + 16), k = lds128(ra + 32);
+    const float dx = g.x - pxf;
+    const u64 dy2 = sub2(bc(g.y), py2);
+    const u64 p2 = power2(c, dx, dy2);
+    const float pA = lo(p2), pB = hi(p2);
+    float GA = ex2_approx(pA), GB = ex2_approx(pB);
+    const u64 a2 = mul2(bc(c.w), pk(GA, GB));
+    float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
+    const bool actA = (pos < lcA) && (pA <= 0.f) && !(alA < ALPHA_MIN);
+    const bool actB = (pos < lcB) && (pB <= 0.f) && !(alB < ALPHA_MIN);
+    f.any = actA || actB;
+    // a pixel the splat was not blended into runs the same code with alpha = G = 0: T, behind and both outputs are then
+    // unchanged / zero
+    alA = actA ? alA : 0.f; alB = actB ? alB : 0.f;
+    GA = actA ? GA : 0.f; GB = actB ? GB : 0.f;
+    f.al2 = pk(alA, alB); f.G2 = pk(GA, GB);
+    const u64 om = sub2(bc(1.f), f.al2);
+    f.ria = pk(rcp_approx(lo(om)), rcp_approx(hi(om)));          // alpha = 0 -> rcp(1) = 1 exactly
+    u64 sj = fma2(bc(k.x), gC0, gA);                             // s_j = gC.rgb_j + gD*depth_j + gA
+    sj = fma2(bc(k.y), gC1, sj);
+    sj = fma2(bc(k.z), gC2, sj);
+    f.sj = fma2(bc(g.z), gD, sj);
+    f.bgr = mul2(bgT, f.ria);                                    // (-T_final/(1-alpha)) * bg.dL_dpixel
+    f.gx = g.x; f.gy = g.y; f.o = c.w;
+    return f;
+}
+
+__device__ __forceinline__ void bwd_back(const BwdFront& f, u64& T2, u64& behind, uint32_t qg, uint32_t qd) {
+    T2 = mul2(T2, f.ria);                                        // T_j = T_{j+1} / (1 - alpha_j)
+    const u64 dchan = mul2(f.al2, T2);                           // d pixel / d channel_j = alpha_j T_j
+    const u64 ds = sub2(f.sj, behind);                           // s_j - (colour behind splat j)
+    const u64 dL_da = fma2(ds, T2, f.bgr);
+    behind = fma2(f.al2, ds, behind);                            // colour behind splat j-1
+    // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6); w = opacity * gda is applied per slot
+    const u64 gda = mul2(f.G2, dL_da);
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(qg), "l"(gda) : "memory");
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(qd), "l"(dchan) : "memory");
+}
+
+__device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_t id) {
+    sts64(sa, f.gx, f.gy);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 8), "r"(id) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
 }
 
 template <int STAGES, int MINB>
@@ -489,62 +567,30 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
             const uint32_t si = s_ids + rs.stage * BATCH * 4;
             uint32_t m[BATCH / 32];
             stage_masks(sr, n, lane, X0f, Y0f, m);
-            int i = BATCH / 32;
-            uint32_t bal = 0, rg = 0, ig = 0, pos0 = 0;
-            for (;;) {
-                if (bal == 0) {          // next non-empty group of 32 records, from the back
-                    do { --i; bal = pick_mask(m, i); } while (bal == 0 && i >= 0);
-                    if (i < 0) break;
-                    rg = sr + i * 32 * REC_BYTES; ig = si + i * 32 * 4; pos0 = (uint32_t)(base + i * 32);
-                }
-                const int jb = 31 - __clz(bal);
-                bal &= ~(1u << jb);
-                const uint32_t ra = rg + jb * REC_BYTES;
-                const float4 g = lds128(ra), c = lds128(ra + 16);
-                const float dx = g.x - pxf;
-                const u64 dy2 = sub2(bc(g.y), py2);
-                const u64 p2 = power2(c, dx, dy2);
-                const float pA = lo(p2), pB = hi(p2);
-                float GA = ex2_approx(pA), GB = ex2_approx(pB);
-                const u64 a2 = mul2(bc(c.w), pk(GA, GB));
-                float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
-                const uint32_t pos = pos0 + jb;
-                const bool actA = (pos < lcA) && (pA <= 0.f) && !(alA < ALPHA_MIN);
-                const bool actB = (pos < lcB) && (pB <= 0.f) && !(alB < ALPHA_MIN);
-                if (!__any_sync(0xFFFFFFFFu, actA || actB)) continue;
-                // a pixel the splat was not blended into runs the same code with alpha = G = 0: T, behind and both
-                // outputs are then unchanged / zero (the pending term of the previous splat is still applied once)
-                alA = actA ? alA : 0.f; alB = actB ? alB : 0.f;
-                GA = actA ? GA : 0.f; GB = actB ? GB : 0.f;
-                const u64 al2 = pk(alA, alB);
-                const float4 k = lds128(ra + 32);
-                const u64 om = sub2(bc(1.f), al2);
-                const u64 ria = pk(rcp_approx(lo(om)), rcp_approx(hi(om)));   // alpha = 0 -> rcp(1) = 1 exactly
-                T2 = mul2(T2, ria);                                   // T_j = T_{j+1} / (1 - alpha_j)
-                const u64 dchan = mul2(al2, T2);                      // d pixel / d channel_j = alpha_j T_j
-                u64 sj = fma2(bc(k.x), gC0, gA);
-                sj = fma2(bc(k.y), gC1, sj);
-                sj = fma2(bc(k.z), gC2, sj);
-                sj = fma2(bc(g.z), gD, sj);
-                const u64 ds = sub2(sj, behind);                      // s_j - (colour behind splat j)
-                const u64 dL_da = fma2(ds, T2, mul2(bgT, ria));       // *T_j, + (-T_final/(1-alpha)) * bg.dL_dpixel
-                behind = fma2(al2, ds, behind);                       // colour behind splat j-1
-                // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6)
-                const u64 gda = mul2(pk(GA, GB), dL_da);              // G * dL/dalpha; w = opacity * gda is applied per slot
-                const uint32_t qo = (uint32_t)nq * 8;
-                asm volatile("st.shared.b64 [%0], %1;" ::"r"(qwG + qo), "l"(gda) : "memory");
-                asm volatile("st.shared.b64 [%0], %1;" ::"r"(qwD + qo), "l"(dchan) : "memory");
-                if (lane == 0) {
-                    const uint32_t sa = slot_base + nq * 16;
-                    sts64(sa, g.x, g.y);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 8), "r"(ld_volatile_s32(ig + jb * 4)) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(c.w) : "memory");
-                }
-                if (++nq == SLOTS) {
-                    __syncwarp();
-                    flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg);
-                    __syncwarp();
-                    nq = 0;
+#pragma unroll
+            for (int i = BATCH / 32 - 1; i >= 0; i--) {
+                uint32_t bal = m[i];
+                const uint32_t rg = sr + i * 32 * REC_BYTES, ig = si + i * 32 * 4, pos0 = (uint32_t)(base + i * 32);
+                // two visits per iteration, from the back: everything but the T / behind recurrences and the queue slot is
+                // independent between them (bwd_front), so the two instruction streams interleave
+                while (bal) {
+                    const int j0 = 31 - __clz(bal);
+                    bal &= ~(1u << j0);
+                    const bool two = bal != 0;
+                    const int j1 = two ? 31 - __clz(bal) : j0;
+                    bal &= ~(1u << j1);
+                    const BwdFront f0 = bwd_front(rg + j0 * REC_BYTES, pos0 + j0, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
+                    const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
+                    if (__any_sync(0xFFFFFFFFu, f0.any)) {
+                        bwd_back(f0, T2, behind, qwG + nq * 8, qwD + nq * 8);
+                        if (lane == 0) put_slot(slot_base + nq * 16, f0, ld_volatile_s32(ig + j0 * 4));
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                    }
+                    if (two && __any_sync(0xFFFFFFFFu, f1.any)) {
+                        bwd_back(f1, T2, behind, qwG + nq * 8, qwD + nq * 8);
+                        if (lane == 0) put_slot(slot_base + nq * 16, f1, ld_volatile_s32(ig + j1 * 4));
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                    }
                 }
             }
         }

@@ -51,3 +51,73 @@ def allreduce_densify_stats(grad_accum: torch.Tensor, denom: torch.Tensor, max_r
     n = grad_accum.numel()
     grad_accum.copy_(packed[:n].view_as(grad_accum)); denom.copy_(packed[n:].view_as(denom))
     dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# all-reduce overlapped with the tail of the step (gs_b200_set_grad_sink)
+# ---------------------------------------------------------------------------------------------------------
+GROUP_WIDTHS = lambda M: (3, 3 * M, 1, 3, 4, 3)          # floats per Gaussian: means3D | shs | opacities | scales | rotations | means2D
+
+
+def chunk_slices(N: int, M: int, first: int, count: int):
+    """(offset, length) of rows first..first+count of each of the six groups inside the packed gradient buffer."""
+    out, base = [], 0
+    for w in GROUP_WIDTHS(M):
+        out.append((base + first * w, count * w))
+        base += N * w
+    return out
+
+
+class OverlappedGradAllReduce:
+    """One logical all-reduce of the packed gradient buffer per step, issued in Gaussian-range chunks from inside the
+    step: the library calls back after each range of its last pass has been enqueued, and the range's six slices are
+    all-reduced on NCCL's stream (ordered after that kernel) while the next range is computed.  Only the last chunk's
+    collective is exposed.
+
+        ar = OverlappedGradAllReduce(params.grads, N, M, nchunks=8)
+        with ar:                       # registers / removes the sink for this thread
+            step_device_pipelined(...)
+        ar.wait()                      # current stream waits for every chunk
+
+    Without an initialised process group (or world 1) it does nothing."""
+
+    def __init__(self, grads: torch.Tensor, N: int, M: int, nchunks: int = 8, group=None):
+        self.grads, self.N, self.M, self.nchunks, self.group = grads, N, M, nchunks, group
+        self.works, self.err = [], None
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        from . import _lib
+        self._lib = _lib
+        self._cb = _lib.GRAD_SINK(self._sink)      # keep the ctypes thunk alive
+
+    def _sink(self, _user, first, count, stream_ptr):
+        try:
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_ptr), device=self.grads.device)):
+                views = [self.grads[o:o + n] for o, n in chunk_slices(self.N, self.M, int(first), int(count))]
+                if hasattr(dist, "_coalescing_manager"):     # one grouped NCCL launch (allreduce_coalesced) for the six slices
+                    with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
+                        for t in views:
+                            dist.all_reduce(t, group=self.group)
+                    self.works.append(cm)
+                else:
+                    for t in views:
+                        self.works.append(dist.all_reduce(t, group=self.group, async_op=True))
+        except BaseException as e:      # never let an exception cross the C frame
+            self.err = e
+
+    def __enter__(self):
+        self.works, self.err = [], None
+        if self.active:
+            self._lib.check(self._lib.lib.gs_b200_set_grad_sink(self._cb, None, self.nchunks))
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._lib.lib.gs_b200_set_grad_sink(self._lib.GRAD_SINK(), None, 1)
+        if self.err is not None and exc[0] is None:
+            raise self.err
+        return False
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []

@@ -143,6 +143,26 @@ class GaussianTrainer:
             world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         total = total_views or V * world
         per_view = torch.zeros(V, device=self.device)
+        # data parallel: the all-reduce of the packed gradients is issued in Gaussian-range chunks from inside the step,
+        # behind its last pass (parallel.OverlappedGradAllReduce); inactive without a process group
+        ar = parallel.OverlappedGradAllReduce(self.grads, self.N, self.M, nchunks=8)
+        ar.__enter__()
+        try:
+            self._run_views(views_np, W, H, ref_images, ref_masks, world, total, per_view, loss_fn)
+        finally:
+            ar.__exit__(None, None, None)
+        loss_sum = per_view.sum()
+        if world > 1:
+            if ar.active:
+                ar.wait()
+            if torch.distributed.is_initialized():
+                torch.distributed.all_reduce(loss_sum)
+        self._optimise(world, loss_sum)
+        return float(loss_sum) / world
+
+    def _run_views(self, views_np, W, H, ref_images, ref_masks, world, total, per_view, loss_fn):
+        p = self.p
+        V = views_np.shape[0]
         if loss_fn is None:
             # native path: the loss and its gradient are CUDA kernels on each view's stream (gs_loss.cu)
             self.activate()
@@ -160,11 +180,9 @@ class GaussianTrainer:
                 dl.copy_(x.grad)
                 per_view[v] = loss.detach()
             self.forward_backward(views_np, W, H, loss_grad_fn)
-        loss_sum = per_view.sum()
-        if world > 1:
-            parallel.allreduce_packed_grads(self.grads)
-            if torch.distributed.is_initialized():
-                torch.distributed.all_reduce(loss_sum)
+
+    def _optimise(self, world, loss_sum):
+        p = self.p
         self.step_count += 1
         lrs = self.learning_rates(self.step_count - 1)
         _lib.check(_lib.lib.gs_b200_adam_step(self.N, self.M, C.c_void_p(lrs.ctypes.data), 0.9, 0.999, 1e-15, self.step_count, 1.0 / world,
@@ -183,7 +201,6 @@ class GaussianTrainer:
                 self.densify_and_prune(p.densify_grad_threshold, 0.005, 4.0, 1.0)
             if s % p.opacity_reset_interval == 0:
                 self.reset_opacity()
-        return float(loss_sum) / world
 
     # ---------------------------------------------------------------- densification (torch-side, infrequent)
     def _rebuild(self, keep_idx, new):

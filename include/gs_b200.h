@@ -223,6 +223,16 @@ int32_t gs_b200_step_device_train(
     float lambda_alpha, float loss_scale, float* dL_dout, float* grads, float* images, int32_t* radii, float* losses,
     int64_t* num_rendered_out, void* stream);
 
+/* Data-parallel hook (no reference counterpart): overlap the gradient all-reduce with the tail of the step.
+ * The last pass of every gs_b200_step_device* call (chain rule from per-view splat gradients to the packed parameter
+ * gradients) is cut into `nchunks` Gaussian ranges; after the kernel of range [first, first+count) has been enqueued
+ * on `stream`, `sink(user, first, count, stream)` is called on the host.  Rows first..first+count of every group of
+ * `grads` are final once the work enqueued on `stream` so far has run, so the callee can start the all-reduce of those
+ * six slices (ordered after an event on `stream`) while the next range is still being computed.
+ * Per calling thread; sink == NULL removes it.  Applies to gs_b200_step_device, _hook and _train. */
+typedef void (*gs_b200_grad_sink)(void* user, int32_t first, int32_t count, void* stream);
+int32_t gs_b200_set_grad_sink(gs_b200_grad_sink sink, void* user, int32_t nchunks);
+
 /* Forward only over V views that share the Gaussians (render nodes: orbit previews, LGM / TRELLIS style multi-view
  * renders — nodes.py:1130-1163, Gen_3D_Modules/LGM/core/gs.py:41-92): one pass over the parameters for all
  * views, then the per-view pipeline.  Exactly one of shs [N,M,3] / colors_precomp [N,3] (LGM passes colours,

@@ -187,6 +187,32 @@ def test_composite_vectorised_equals_sequential(kind, deg, W, H):
     assert int((r[:, 1] - r[:, 0]).sum()) == k.size
 
 
+@pytest.mark.parametrize("kind,n,W,H", [("D0", 3000, 200, 120), ("D1", 2500, 160, 96)])
+def test_vectorised_key_duplication_equals_the_loop_and_tile_subset_composite(kind, n, W, H):
+    """The two helpers the full-size GPU parity test relies on: keys/values without the per-Gaussian Python loop, and
+    the composite restricted to a subset of tiles (identical pixels inside the subset, background outside)."""
+    cl = O.make_cloud(kind, n, 1, seed=5)
+    st = _settings(W, H, 5, 30, deg=1, bg=(0.1, 0.2, 0.3))
+    pre = O.preprocess(cl["means3D"], cl["scales"], cl["rotations"], cl["opacities"], cl["shs"], None, None, None, st)
+    k0, v0 = O.duplicate_with_keys(pre)
+    k1, v1 = O.duplicate_with_keys_vectorised(pre)
+    assert np.array_equal(k0, k1) and np.array_equal(v0, v1)
+    sk, sv = O.sort_pairs(k1, v1)
+    gx, gy = pre["grid"]
+    ranges = O.identify_tile_ranges(sk, gx * gy)
+    full = O.composite(pre, sv, ranges, st)
+    subset = [t for t in range(gx * gy) if t % 3 == 1]
+    part = O.composite(pre, sv, ranges, st, tiles=subset)
+    mask = torch.zeros(H, W, dtype=torch.bool)
+    for t in subset:
+        yy, xx = O._tile_pixels(t, gx, W, H, torch.float32)
+        mask[yy, xx] = True
+    for a, b in zip(full[:3], part[:3]):
+        assert torch.equal(a[:, mask], b[:, mask])
+    assert torch.equal(full[3][mask], part[3][mask]) and torch.equal(full[4][mask], part[4][mask])
+    assert torch.equal(part[0][:, ~mask], st.bg[:, None].expand(3, int((~mask).sum())).to(part[0].dtype))
+
+
 def test_sort_is_stable_for_equal_keys():
     keys = np.array([5, 3, 5, 3, 5], dtype=np.uint64)
     vals = np.arange(5, dtype=np.uint32)
