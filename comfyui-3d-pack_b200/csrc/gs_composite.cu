@@ -40,8 +40,8 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int NMATH = 4;                 // math warps per CTA
-constexpr int NTHREADS = (NMATH + 1) * 32;
+constexpr int NMATH = 4;                 // warps per CTA, one per 8x8 quadrant
+constexpr int NTHREADS = NMATH * 32;
 constexpr int BATCH = 128;               // records per ring stage
 constexpr uint32_t REC_BYTES = 48;
 constexpr uint32_t STAGE_BYTES = BATCH * REC_BYTES;
@@ -247,11 +247,11 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
                          float* __restrict__ out_depth, float* __restrict__ out_alpha,
                          uint32_t* __restrict__ n_contrib, float* __restrict__ final_T) {
     __shared__ __align__(128) unsigned char s_rec_raw[STAGES * STAGE_BYTES];
-    __shared__ __align__(8) u64 s_full[STAGES], s_empty[STAGES];
-    __shared__ uint32_t s_done, s_stop;
+    __shared__ __align__(8) u64 s_full[STAGES];
+    __shared__ uint32_t s_cnt[STAGES], s_stop;
     const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(s_rec_raw);
-    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(s_full), a_empty = (uint32_t)__cvta_generic_to_shared(s_empty);
-    const uint32_t a_done = (uint32_t)__cvta_generic_to_shared(&s_done), a_stop = (uint32_t)__cvta_generic_to_shared(&s_stop);
+    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(s_full);
+    const uint32_t a_stop = (uint32_t)__cvta_generic_to_shared(&s_stop);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * va.tiles_x + blockIdx.x;
     const uint32_t start = ranges[2 * tile], end = ranges[2 * tile + 1];
@@ -259,34 +259,16 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
     const int nb = (len + BATCH - 1) / BATCH;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, NMATH); }
-        s_done = 0; s_stop = 0xFFFFFFFFu;
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); s_cnt[i] = 0; }
+        s_stop = 0xFFFFFFFFu;
         mbar_fence_init();
     }
     __syncthreads();
+    // first fill of the ring: warp w gathers batch w (afterwards the LAST warp to finish a stage refills it)
+    if (warp < STAGES && warp < nb)
+        produce_stage<false>(recs, point_list + start + warp * BATCH, min(BATCH, len - warp * BATCH), s_rec + warp * STAGE_BYTES, 0u,
+                             a_full + 8 * warp, lane);
 
-    if (warp == NMATH) {
-        // ------------------------------ producer warp ------------------------------
-        RingState rs;
-        for (int b = 0; b < nb; b++) {
-            if (b >= STAGES) mbar_wait(a_empty + 8 * rs.stage, rs.phase ^ 1u);
-            const uint32_t done = __shfl_sync(0xFFFFFFFFu, ld_volatile_s32(a_done), 0);
-            if (done == NMATH) {         // every pixel of the tile has terminated: hand the math warps the stop batch
-                if (lane == 0) {
-                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_stop), "r"((uint32_t)b) : "memory");
-                    mbar_arrive(a_full + 8 * rs.stage);
-                }
-                break;
-            }
-            const int n = min(BATCH, len - b * BATCH);
-            produce_stage<false>(recs, point_list + start + b * BATCH, n, s_rec + rs.stage * STAGE_BYTES, 0u,
-                                 a_full + 8 * rs.stage, lane);
-            rs.advance(STAGES);
-        }
-        return;
-    }
-
-    // ------------------------------ math warps ------------------------------
     const int X0 = blockIdx.x * GS_TILE + 8 * (warp & 1), Y0 = blockIdx.y * GS_TILE + 8 * (warp >> 1);
     const int px = X0 + (lane & 7), pyA = Y0 + (lane >> 3), pyB = pyA + 4;
     const bool inA = px < va.W && pyA < va.H, inB = px < va.W && pyB < va.H;
@@ -301,7 +283,6 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
     u64 C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D2 = bc(0.f), A2 = bc(0.f);
     uint32_t lastA = 0, lastB = 0;
     bool warp_done = __all_sync(0xFFFFFFFFu, !inA && !inB);
-    if (warp_done && lane == 0) atomicAdd(&s_done, 1u);
 
     RingState rs;
     for (int b = 0; b < nb; b++) {
@@ -338,10 +319,28 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
                 }
                 if (__all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
             }
-            if (warp_done && lane == 0) atomicAdd(&s_done, 1u);
         }
+        // release the stage; the last of the four warps to do so refills it with batch b + STAGES.  Each release carries
+        // the warp's "all my pixels have terminated" bit: when all four say so the tile is finished, nothing is gathered
+        // any more and the stop batch is published (a function of b only, so concurrent refills cannot disagree).
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty + 8 * rs.stage);
+        uint32_t tot = 0;
+        if (lane == 0) { __threadfence_block(); tot = atomicAdd(&s_cnt[rs.stage], 1u + (warp_done ? 0x100u : 0u)) + 1u + (warp_done ? 0x100u : 0u); }
+        tot = __shfl_sync(0xFFFFFFFFu, tot, 0);
+        if ((tot & 0xFFu) == NMATH) {
+            const int nbatch = b + STAGES;
+            if (lane == 0) s_cnt[rs.stage] = 0;
+            __syncwarp();
+            if (nbatch < nb) {
+                if ((tot >> 8) == NMATH) {
+                    if (lane == 0) { atomicMin(&s_stop, (uint32_t)nbatch); __threadfence_block(); mbar_arrive(a_full + 8 * rs.stage); }
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
+                    produce_stage<false>(recs, point_list + start + nbatch * BATCH, min(BATCH, len - nbatch * BATCH),
+                                         s_rec + rs.stage * STAGE_BYTES, 0u, a_full + 8 * rs.stage, lane);
+                }
+            }
+        }
         rs.advance(STAGES);
     }
     const u64 T2 = pk(TA, TB);
@@ -365,60 +364,77 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
 // =================================================================================================
 // backward
 // =================================================================================================
-constexpr int SLOTS = 16;                          // queued visits per flush
-constexpr uint32_t QROW = (SLOTS + 1) * 8;         // bytes per pixel row of the queue: SLOTS float2 + 8 B pad (bank spread)
-constexpr uint32_t QWARP = 64 * QROW;              // queue bytes per math warp: 32 lane rows x {G dL/dalpha pair, alpha T pair}
+// queue geometry for SLOTS queued visits per flush (8 or 16): a row = SLOTS float2 + 8 B pad (bank spread), 32 lane rows
+// per array, two arrays (G dL/dalpha pairs, alpha T pairs) per warp
+template <int SLOTS> struct QGeom {
+    static constexpr uint32_t ROW = (SLOTS + 1) * 8;
+    static constexpr uint32_t WARP = 64 * ROW;
+    static constexpr int PARTS = 32 / SLOTS;       // lanes = (slot, part); a part owns SLOTS consecutive lane rows
+};
 
-// Second phase of the backward: lanes = (slot, half of the lanes' pixel pairs).  Each lane sums, over its 16 pixel
-// pairs (pixel A = (x, y), pixel B = (x, y+4) of first-phase lane 8y+x), the queued (G*dL/dalpha, alpha*T) of its slot
-// against pixel-local coordinates and the per-pixel upstream gradients.
+// Second phase of the backward: lanes = (slot, part).  Each lane sums, over its SLOTS pixel pairs (pixel A = (x, y),
+// pixel B = (x, y+4) of first-phase lane 8y+x), the queued (G*dL/dalpha, alpha*T) of its slot against pixel-local
+// coordinates and the per-pixel upstream gradients; the parts are then added with shfl.xor.
+template <int SLOTS>
 __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, uint32_t slot_base, int nq, int lane,
                                          float Xc, float Yc, SplatGrad* __restrict__ sg) {
-    const int slot = lane & (SLOTS - 1), part = lane >> 4;
-    const uint32_t qg = q_base + slot * 8 + part * 16 * QROW, qd = qg + 32 * QROW;
-    const uint32_t ca = coef_base + part * 16 * 32;
+    using Q = QGeom<SLOTS>;
+    const int slot = lane & (SLOTS - 1), part = lane / SLOTS;
+    const uint32_t qg = q_base + slot * 8 + part * SLOTS * Q::ROW, qd = qg + 32 * Q::ROW;
+    const uint32_t ca = coef_base + part * SLOTS * 32;
     float M0 = 0.f, M1 = 0.f, M2 = 0.f, My = 0.f, Mxy = 0.f, Myy = 0.f;
     u64 Cr2 = bc(0.f), Cg2 = bc(0.f), Cb2 = bc(0.f), Cd2 = bc(0.f);       // (pixel A, pixel B) halves, added at the end
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < SLOTS / 8; r++) {
         u64 s0 = bc(0.f), s1 = bc(0.f), s2 = bc(0.f);                       // row sums of w, w*LX, w*LX^2 for (row of A, row of B)
 #pragma unroll
         for (int x = 0; x < 8; x++) {
             const int p = r * 8 + x;
             u64 w, d, c0, c1, c2, cd;
-            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(qg + p * QROW));
-            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(d) : "r"(qd + p * QROW));
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(qg + p * Q::ROW));
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(d) : "r"(qd + p * Q::ROW));
             asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(ca + p * 32));
             asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(c2), "=l"(cd) : "r"(ca + p * 32 + 16));
             const float LX = (float)x - 3.5f;
             s0 = add2(s0, w); s1 = fma2(w, bc(LX), s1); s2 = fma2(w, bc(LX * LX), s2);
             Cr2 = fma2(d, c0, Cr2); Cg2 = fma2(d, c1, Cg2); Cb2 = fma2(d, c2, Cb2); Cd2 = fma2(d, cd, Cd2);
         }
-        const float LYA = (float)(part * 2 + r) - 3.5f, LYB = LYA + 4.0f;
+        const float LYA = (float)(part * (SLOTS / 8) + r) - 3.5f, LYB = LYA + 4.0f;
         const float a0 = lo(s0), b0 = hi(s0), a1 = lo(s1), b1 = hi(s1);
         M0 += a0 + b0; M1 += a1 + b1; M2 += lo(s2) + hi(s2);
         My = fmaf(a0, LYA, My); Mxy = fmaf(a1, LYA, Mxy); Myy = fmaf(a0, LYA * LYA, Myy);
         My = fmaf(b0, LYB, My); Mxy = fmaf(b1, LYB, Mxy); Myy = fmaf(b0, LYB * LYB, Myy);
     }
     float Cr = lo(Cr2) + hi(Cr2), Cg = lo(Cg2) + hi(Cg2), Cb = lo(Cb2) + hi(Cb2), Cd = lo(Cd2) + hi(Cd2);
-#define XADD(v) v += __shfl_xor_sync(0xFFFFFFFFu, v, 16)
-    XADD(M0); XADD(M1); XADD(M2); XADD(My); XADD(Mxy); XADD(Myy); XADD(Cd); XADD(Cr); XADD(Cg); XADD(Cb);
+#pragma unroll
+    for (int o = 16; o >= SLOTS; o >>= 1) {
+#define XADD(v) v += __shfl_xor_sync(0xFFFFFFFFu, v, o)
+        XADD(M0); XADD(M1); XADD(M2); XADD(My); XADD(Mxy); XADD(Myy); XADD(Cd); XADD(Cr); XADD(Cg); XADD(Cb);
 #undef XADD
+    }
     if (slot < nq) {
         const float4 si = lds128(slot_base + slot * 16);        // mean2D.x, mean2D.y, id, opacity
         float* dst = reinterpret_cast<float*>(sg + __float_as_uint(si.z));
         // pixel = centre + L, d = mean2D - pixel = u - L with u = mean2D - centre
         const float u = si.x - Xc, v = si.y - Yc, o = si.w;
-        if (part == 0) {
-            atomicAdd(dst + 0, o * (u * M0 - M1));                                   // sum w dx
-            atomicAdd(dst + 1, o * (v * M0 - My));                                   // sum w dy
-            atomicAdd(dst + 2, Cd);                                                  // dL/ddepth
-            atomicAdd(dst + 4, o * (fmaf(u, fmaf(u, M0, -2.f * M1), M2)));           // sum w dx dx
-            atomicAdd(dst + 5, o * (fmaf(u, fmaf(v, M0, -My), fmaf(-v, M1, Mxy))));  // sum w dx dy
-        } else {
-            atomicAdd(dst + 6, o * (fmaf(v, fmaf(v, M0, -2.f * My), Myy)));          // sum w dy dy
-            atomicAdd(dst + 7, M0);                                                  // dL/dopacity (sum G dL/dalpha)
-            atomicAdd(dst + 8, Cr); atomicAdd(dst + 9, Cg); atomicAdd(dst + 10, Cb); // dL/drgb
+        // the ten sums of the splat, in SplatGrad float offsets 0,1,2 | 4,5,6,7 | 8,9,10; the parts share the red's
+        const float val[10] = {o * (u * M0 - M1),                                  // sum w dx
+                               o * (v * M0 - My),                                  // sum w dy
+                               Cd,                                                 // dL/ddepth
+                               o * (fmaf(u, fmaf(u, M0, -2.f * M1), M2)),          // sum w dx dx
+                               o * (fmaf(u, fmaf(v, M0, -My), fmaf(-v, M1, Mxy))), // sum w dx dy
+                               o * (fmaf(v, fmaf(v, M0, -2.f * My), Myy)),         // sum w dy dy
+                               M0,                                                 // dL/dopacity (sum G dL/dalpha)
+                               Cr, Cg, Cb};                                        // dL/drgb
+#pragma unroll
+        for (int k = 0; k < (10 + Q::PARTS - 1) / Q::PARTS; k++) {
+            float x = 0.f; int off = -1;
+#pragma unroll
+            for (int q = 0; q < Q::PARTS; q++) {
+                const int vi = k * Q::PARTS + q;
+                if (vi < 10 && part == q) { x = val[vi]; off = vi + (vi >= 3); }
+            }
+            if (off >= 0) atomicAdd(dst + off, x);
         }
     }
 }
@@ -474,22 +490,24 @@ __device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
 }
 
-template <int STAGES, int MINB>
+template <int STAGES, int SLOTS, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                           const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
                           const float* __restrict__ final_T, const float* __restrict__ dL_dcolor,
                           const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                           SplatGrad* __restrict__ sg) {
-    // dynamic shared memory (> 48 KB): ring | queue | per-pixel upstream gradients | slot info | ids | barriers | wmax
+    using Q = QGeom<SLOTS>;
+    // dynamic shared memory: ring | queue | per-pixel upstream gradients | slot info | ids | barriers | counters | wmax
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t s_q = s_rec + STAGES * STAGE_BYTES;
-    const uint32_t s_coef = s_q + NMATH * QWARP;
+    const uint32_t s_coef = s_q + NMATH * Q::WARP;
     const uint32_t s_slot = s_coef + NMATH * 64 * 16;
     const uint32_t s_ids = s_slot + NMATH * SLOTS * 16;
-    const uint32_t a_full = s_ids + STAGES * BATCH * 4, a_empty = a_full + 8 * STAGES;
-    volatile uint32_t* s_wmax = reinterpret_cast<volatile uint32_t*>(smem + (a_empty + 8 * STAGES - s_rec));
+    const uint32_t a_full = s_ids + STAGES * BATCH * 4;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + (a_full + 8 * STAGES - s_rec));
+    volatile uint32_t* s_wmax = s_cnt + STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.y * va.tiles_x + blockIdx.x;
     const uint32_t start = ranges[2 * tile], end = ranges[2 * tile + 1];
@@ -497,39 +515,30 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
 
     const int X0 = blockIdx.x * GS_TILE + 8 * (warp & 1), Y0 = blockIdx.y * GS_TILE + 8 * (warp >> 1);
     const int px = X0 + (lane & 7), pyA = Y0 + (lane >> 3), pyB = pyA + 4;
-    const bool math = warp < NMATH;
-    const bool inA = math && px < va.W && pyA < va.H, inB = math && px < va.W && pyB < va.H;
+    const bool inA = px < va.W && pyA < va.H, inB = px < va.W && pyB < va.H;
     const size_t plane = (size_t)va.W * va.H;
     const size_t pixA = (size_t)pyA * va.W + px, pixB = (size_t)pyB * va.W + px;
     const uint32_t lcA = inA ? n_contrib[pixA] : 0u, lcB = inB ? n_contrib[pixB] : 0u;
     uint32_t wmax = max(lcA, lcB);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
-    if (math && lane == 0) s_wmax[warp] = wmax;
+    if (lane == 0) s_wmax[warp] = wmax;
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, NMATH); }
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); s_cnt[i] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
     const uint32_t nproc = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));   // list positions 1..nproc were blended
     if (nproc == 0) return;
     const int nb = (int)((nproc + BATCH - 1) / BATCH);
+    // stages are gathered from the back of the list: iteration `it` holds list positions [(nb-1-it)*BATCH, +BATCH)
+    auto produce = [&](int it, uint32_t stage) {
+        const int base = (nb - 1 - it) * BATCH;
+        produce_stage<true>(recs, point_list + start + base, min(BATCH, (int)nproc - base), s_rec + stage * STAGE_BYTES,
+                            s_ids + stage * BATCH * 4, a_full + 8 * stage, lane);
+    };
+    if (warp < STAGES && warp < nb) produce(warp, warp);       // first fill; afterwards the last warp to finish a stage refills it
 
-    if (!math) {
-        // ------------------------------ producer warp: stages from the back of the list ------------------------------
-        RingState rs;
-        for (int it = 0; it < nb; it++) {
-            if (it >= STAGES) mbar_wait(a_empty + 8 * rs.stage, rs.phase ^ 1u);
-            const int base = (nb - 1 - it) * BATCH;
-            const int n = min(BATCH, (int)nproc - base);
-            produce_stage<true>(recs, point_list + start + base, n, s_rec + rs.stage * STAGE_BYTES,
-                                s_ids + rs.stage * BATCH * 4, a_full + 8 * rs.stage, lane);
-            rs.advance(STAGES);
-        }
-        return;
-    }
-
-    // ------------------------------ math warps ------------------------------
     const float pxf = (float)px;
     const u64 py2 = pk((float)pyA, (float)pyB);
     const float X0f = (float)X0, Y0f = (float)Y0;
@@ -541,12 +550,12 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     const u64 gC0 = pk(gC0A, gC0B), gC1 = pk(gC1A, gC1B), gC2 = pk(gC2A, gC2B), gD = pk(gDA, gDB), gA = pk(gAA, gAB);
     const u64 bgT = pk(-TfA * (bg0 * gC0A + bg1 * gC1A + bg2 * gC2A), -TfB * (bg0 * gC0B + bg1 * gC1B + bg2 * gC2B));
 
-    const uint32_t q_base = s_q + warp * QWARP;
+    const uint32_t q_base = s_q + warp * Q::WARP;
     const uint32_t coef_base = s_coef + warp * 64 * 16;
     const uint32_t slot_base = s_slot + warp * SLOTS * 16;
     sts128(coef_base + lane * 32, make_float4(gC0A, gC0B, gC1A, gC1B));           // (A, B) pairs per channel: the
     sts128(coef_base + lane * 32 + 16, make_float4(gC2A, gC2B, gDA, gDB));         // second phase multiplies them packed
-    const uint32_t qwG = q_base + lane * QROW, qwD = qwG + 32 * QROW;     // this lane's rows of the two queue arrays
+    const uint32_t qwG = q_base + lane * Q::ROW, qwD = qwG + 32 * Q::ROW;     // this lane's rows of the two queue arrays
     const float Xc = X0f + 3.5f, Yc = Y0f + 3.5f;
     __syncwarp();
 
@@ -584,29 +593,40 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                     if (__any_sync(0xFFFFFFFFu, f0.any)) {
                         bwd_back(f0, T2, behind, qwG + nq * 8, qwD + nq * 8);
                         if (lane == 0) put_slot(slot_base + nq * 16, f0, ld_volatile_s32(ig + j0 * 4));
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
                     }
                     if (two && __any_sync(0xFFFFFFFFu, f1.any)) {
                         bwd_back(f1, T2, behind, qwG + nq * 8, qwD + nq * 8);
                         if (lane == 0) put_slot(slot_base + nq * 16, f1, ld_volatile_s32(ig + j1 * 4));
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
                     }
                 }
             }
         }
+        // release the stage; the last of the four warps to do so refills it
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty + 8 * rs.stage);
+        uint32_t tot = 0;
+        if (lane == 0) { __threadfence_block(); tot = atomicAdd(&s_cnt[rs.stage], 1u) + 1u; }
+        tot = __shfl_sync(0xFFFFFFFFu, tot, 0);
+        if (tot == NMATH) {
+            if (lane == 0) s_cnt[rs.stage] = 0;
+            __syncwarp();
+            if (it + STAGES < nb) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
+                produce(it + STAGES, rs.stage);
+            }
+        }
         rs.advance(STAGES);
     }
     if (nq > 0) {
         __syncwarp();
-        flush_queue(q_base, coef_base, slot_base, nq, lane, Xc, Yc, sg);
+        flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, sg);
     }
 }
 
-constexpr size_t bwd_smem_bytes(int stages) {
-    return (size_t)stages * STAGE_BYTES + NMATH * QWARP + NMATH * 64 * 16 + NMATH * SLOTS * 16 + (size_t)stages * BATCH * 4 +
-           16 * (size_t)stages + 16;
+constexpr size_t bwd_smem_bytes(int stages, int slots) {
+    return (size_t)stages * STAGE_BYTES + NMATH * 64 * (size_t)(slots + 1) * 8 + NMATH * 64 * 16 + NMATH * (size_t)slots * 16 +
+           (size_t)stages * BATCH * 4 + 8 * (size_t)stages + 4 * (size_t)stages + 16;
 }
 
 int env_int(const char* name, int dflt) {
@@ -658,16 +678,17 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     if (use_r1()) return gs_launch_render_backward_r1(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s);
     dim3 grid(va.tiles_x, va.tiles_y);
     static const int stages = env_int("GS_B200_BWD_STAGES", 2);
-    static const int occ = env_int("GS_B200_BWD_OCC", 4);
-#define BWD(ST, OC)                                                                                                        \
+    static const int slots = env_int("GS_B200_BWD_SLOTS", 8);
+    static const int occ = env_int("GS_B200_BWD_OCC", 6);
+#define BWD(ST, SL, OC)                                                                                                    \
     do {                                                                                                                   \
-        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, OC>,                            \
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST)); \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC>,                        \
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, SL)); \
         GS_CUDA_CHECK(attr);                                                                                               \
-        composite_backward_kernel<ST, OC><<<grid, NTHREADS, bwd_smem_bytes(ST), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+        composite_backward_kernel<ST, SL, OC><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
-    if (stages == 3) { if (occ >= 4) BWD(3, 4); else BWD(3, 3); }
-    else             { if (occ >= 5) BWD(2, 5); else if (occ == 3) BWD(2, 3); else BWD(2, 4); }
+    if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
+    else             { if (stages == 3) BWD(3, 8, 5); else if (occ >= 6) BWD(2, 8, 6); else if (occ == 5) BWD(2, 8, 5); else BWD(2, 8, 4); }
 #undef BWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());

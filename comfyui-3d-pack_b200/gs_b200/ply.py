@@ -65,3 +65,49 @@ def read_gs_ply(path, device="cpu"):
 def max_sh_degree_from_properties(n_rest: int) -> int:
     """calculate_max_sh_degree_from_gs_ply (mesh_utils.py:346-350)."""
     return int(((n_rest + 3) / 3) ** 0.5 - 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# axis switch / rescale of a Gaussian cloud, on the device the tensors live on
+# ---------------------------------------------------------------------------------------------------------
+def quaternion_to_axis_angle(q: torch.Tensor) -> torch.Tensor:
+    """(w, x, y, z) -> axis * angle, the convention of kornia.geometry.conversions.quaternion_to_axis_angle (kornia >= 0.7,
+    the un-vendored package mesh_utils.py:3-6 imports; restated): angle in (-pi, pi], 2 * xyz for a zero vector part."""
+    w, xyz = q[..., 0], q[..., 1:]
+    s2 = (xyz * xyz).sum(-1)
+    s = torch.sqrt(s2)
+    two_theta = 2.0 * torch.where(w < 0, torch.atan2(-s, -w), torch.atan2(s, w))
+    k = torch.where(s2 > 0, two_theta / s, torch.full_like(s, 2.0))
+    return xyz * k[..., None]
+
+
+def axis_angle_to_quaternion(a: torch.Tensor) -> torch.Tensor:
+    """axis * angle -> (w, x, y, z), as kornia.geometry.conversions.axis_angle_to_quaternion (restated)."""
+    t2 = (a * a).sum(-1)
+    t = torch.sqrt(t2)
+    half = 0.5 * t
+    pos = t2 > 0
+    k = torch.where(pos, torch.sin(half) / t, torch.full_like(t, 0.5))
+    w = torch.where(pos, torch.cos(half), torch.ones_like(t))
+    return torch.cat([w[..., None], a * k[..., None]], dim=-1)
+
+
+def switch_axis_and_scale(fields: dict, target_axis, target_scale, coordinate_invert_count: int) -> dict:
+    """switch_ply_axis_and_scale (mesh_processer/mesh_utils.py:446-472) without its numpy <-> CUDA round trips: every
+    tensor stays on the device it is on.  `fields` = dict(xyz [N,3], shs [N,M,3], opacity [N,1], scaling [N,3] (raw log
+    scales), rotation [N,4] (raw w,x,y,z)) as `read_gs_ply` / `unpack_rows` return; returns a new dict.
+      xyz      <- (xyz * target_scale)[:, target_axis]
+      scaling  <- scaling[:, target_axis]                      (the reference permutes the raw log-scales, no rescale)
+      rotation <- quaternion of (axis_angle * target_scale)[:, target_axis], negated when the handedness flips an odd
+                  number of times; SHs and opacity are untouched."""
+    dev = fields["xyz"].device
+    axis = torch.as_tensor(list(target_axis), dtype=torch.long, device=dev)
+    scale = torch.as_tensor(list(target_scale), dtype=torch.float32, device=dev)
+    out = dict(fields)
+    out["xyz"] = (fields["xyz"].float() * scale)[:, axis].contiguous()
+    out["scaling"] = fields["scaling"].float()[:, axis].contiguous()
+    aa = (quaternion_to_axis_angle(fields["rotation"].float()) * scale)[:, axis]
+    if coordinate_invert_count % 2 != 0:
+        aa = -aa
+    out["rotation"] = axis_angle_to_quaternion(aa).contiguous()
+    return out

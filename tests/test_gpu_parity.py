@@ -485,7 +485,9 @@ def test_config1_full_frame_keys_and_sampled_tile_composite_match_the_oracle(dev
             R.set_tile_culling(0)
             fs = R.forward_with_state(rs, cloud["means3D"], cloud["opacities"], shs=cloud["shs"], scales=cloud["scales"],
                                       rotations=cloud["rotations"])
-            assert torch.equal(fs["radii"].cpu(), pre["radii"])
+            rad_bad = int((fs["radii"].cpu() != pre["radii"]).sum())
+            stats.append(dict(view=v, what="radii", differ=rad_bad, pairs_gpu=int(fs["num_rendered"]), pairs_oracle=int(skeys.size)))
+            assert rad_bad == 0, f"view {v}: {rad_bad} radii differ"
             assert fs["num_rendered"] == skeys.size
             assert np.array_equal(fs["sorted_keys"].cpu().numpy().view(np.uint64), skeys)
             assert np.array_equal(fs["point_list"].cpu().numpy().view(np.uint32), svals)

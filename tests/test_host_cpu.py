@@ -159,3 +159,39 @@ def test_gs_ply_wire_format_roundtrip_and_property_order(tmp_path):
     rows = ply.pack_rows(**d)
     assert float(rows[5, 9 + 1 * 15 + 3]) == float(d["shs"][5, 4, 1])          # f_rest_{c*(M-1)+k} = coeff k+1 of channel c
     assert ply.max_sh_degree_from_properties(45) == 3 and ply.max_sh_degree_from_properties(0) == 0
+
+
+def test_switch_axis_and_scale_matches_the_reference_sequence():
+    """gs_b200.ply.switch_axis_and_scale against a step-by-step restatement of switch_ply_axis_and_scale
+    (mesh_processer/mesh_utils.py:446-472) in numpy, including the in-place column permutation of switch_vector_axis
+    (:433-443) and the odd-inversion sign flip; quaternion <-> axis-angle round trip is the identity on unit quaternions."""
+    import numpy as np
+    import torch
+    from gs_b200 import ply
+    rng = np.random.RandomState(0)
+    n = 257
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[0] = [1, 0, 0, 0]; q[1] = [-1, 0, 0, 0]                       # zero vector part: the k = 2 / k = 0.5 branches
+    f = dict(xyz=torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)), shs=torch.zeros(n, 4, 3), opacity=torch.zeros(n, 1),
+             scaling=torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)), rotation=torch.from_numpy(q.astype(np.float32)))
+    rt = ply.axis_angle_to_quaternion(ply.quaternion_to_axis_angle(f["rotation"]))
+    same = torch.minimum((rt - f["rotation"]).abs().amax(1), (rt + f["rotation"]).abs().amax(1))     # q and -q are one rotation
+    assert float(same.max()) < 1e-5
+    for axis, scale, inv in (([2, 0, 1], [1.0, -1.0, 1.0], 1), ([0, 2, 1], [2.0, 2.0, 2.0], 0), ([0, 1, 2], [1.0, 1.0, 1.0], 2)):
+        out = ply.switch_axis_and_scale(f, axis, scale, inv)
+        sc = np.asarray(scale, dtype=np.float32)
+        xyz = (f["xyz"].numpy() * sc)[:, axis]
+        w, v = q[:, 0], q[:, 1:]
+        s = np.linalg.norm(v, axis=1)
+        two_theta = 2 * np.where(w < 0, np.arctan2(-s, -w), np.arctan2(s, w))
+        k = np.where(s > 0, two_theta / np.where(s > 0, s, 1), 2.0)
+        aa = ((v * k[:, None]) * sc)[:, axis]
+        if inv % 2:
+            aa = -aa
+        t = np.linalg.norm(aa, axis=1)
+        kk = np.where(t > 0, np.sin(0.5 * t) / np.where(t > 0, t, 1), 0.5)
+        ref_q = np.concatenate([np.where(t > 0, np.cos(0.5 * t), 1.0)[:, None], aa * kk[:, None]], 1)
+        assert np.allclose(out["xyz"].numpy(), xyz, atol=1e-6)
+        assert np.array_equal(out["scaling"].numpy(), f["scaling"].numpy()[:, axis])
+        assert np.allclose(out["rotation"].numpy(), ref_q, atol=2e-6)
+        assert out["shs"] is f["shs"] and out["opacity"] is f["opacity"]
