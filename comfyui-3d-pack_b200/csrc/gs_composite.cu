@@ -53,6 +53,9 @@ __device__ __forceinline__ u64 bc(float a) { return pk(a, a); }
 __device__ __forceinline__ float lo(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float hi(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// acc = a * b + acc with the accumulator as a read-write operand (keeps loop-carried sums in one register pair)
+__device__ __forceinline__ void fma2_acc(u64& acc, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void add2_acc(u64& acc, u64 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -101,6 +104,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {      // 16-byte aligned global address
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_volatile_s32(uint32_t addr) {
     uint32_t v;
@@ -201,26 +207,26 @@ __device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs,
 }
 
 // ---- one visit of the forward, split into a state-free front half and the sequential blend ------------------------
-struct FwdFront { u64 al2; float4 g; bool liveA, liveB; };
+struct FwdFront { u64 al2, p2; float gz; };
 
 __device__ __forceinline__ FwdFront fwd_front(uint32_t ra, float pxf, float pyfA, float pyfB) {
     FwdFront f;
-    f.g = lds128(ra);
-    const float4 c = lds128(ra + 16);
-    const float dx = f.g.x - pxf;
-    const u64 dy2 = sub2(bc(f.g.y), pk(pyfA, pyfB));
-    const u64 p2 = power2(c, dx, dy2);
-    const float pA = lo(p2), pB = hi(p2);
-    const u64 a2 = mul2(bc(c.w), pk(ex2_approx(pA), ex2_approx(pB)));
-    const float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
-    f.al2 = pk(alA, alB);
-    f.liveA = (pA <= 0.f) && !(alA < ALPHA_MIN);       // a terminated pixel has a NaN power
-    f.liveB = (pB <= 0.f) && !(alB < ALPHA_MIN);
+    const float4 g = lds128(ra), c = lds128(ra + 16);
+    const float dx = g.x - pxf;
+    const u64 dy2 = sub2(bc(g.y), pk(pyfA, pyfB));
+    f.p2 = power2(c, dx, dy2);
+    const u64 a2 = mul2(bc(c.w), pk(ex2_approx(lo(f.p2)), ex2_approx(hi(f.p2))));
+    f.al2 = pk(fminf(0.99f, lo(a2)), fminf(0.99f, hi(a2)));
+    f.gz = g.z;
     return f;
 }
+// contributes iff power <= 0 (a terminated pixel has a NaN power) and alpha >= 1/255
+__device__ __forceinline__ bool fwd_live(float p, float al) { return (p <= 0.f) && !(al < ALPHA_MIN); }
+
+struct FwdAcc { float c0a, c0b, c1a, c1b, c2a, c2b, da, db, aa, ab; };
 
 __device__ __forceinline__ void fwd_back(const FwdFront& f, bool liveA, bool liveB, uint32_t ra, uint32_t pos, float& TA,
-                                         float& TB, u64& C0, u64& C1, u64& C2, u64& D2, u64& A2, uint32_t& lastA, uint32_t& lastB,
+                                         float& TB, FwdAcc& acc, uint32_t& lastA, uint32_t& lastB,
                                          float& pyfA, float& pyfB) {
     const u64 T2 = pk(TA, TB);
     const u64 tt2 = mul2(T2, sub2(bc(1.f), f.al2));          // T * (1 - alpha)
@@ -229,8 +235,12 @@ __device__ __forceinline__ void fwd_back(const FwdFront& f, bool liveA, bool liv
     const u64 w2raw = mul2(f.al2, T2);
     const u64 w2 = pk(blA ? lo(w2raw) : 0.f, blB ? hi(w2raw) : 0.f);
     const float4 k = lds128(ra + 32);
-    C0 = fma2(bc(k.x), w2, C0); C1 = fma2(bc(k.y), w2, C1); C2 = fma2(bc(k.z), w2, C2);
-    D2 = fma2(bc(f.g.z), w2, D2); A2 = add2(A2, w2);
+    u64 t;
+    t = fma2(bc(k.x), w2, pk(acc.c0a, acc.c0b)); acc.c0a = lo(t); acc.c0b = hi(t);
+    t = fma2(bc(k.y), w2, pk(acc.c1a, acc.c1b)); acc.c1a = lo(t); acc.c1b = hi(t);
+    t = fma2(bc(k.z), w2, pk(acc.c2a, acc.c2b)); acc.c2a = lo(t); acc.c2b = hi(t);
+    t = fma2(bc(f.gz), w2, pk(acc.da, acc.db)); acc.da = lo(t); acc.db = hi(t);
+    t = add2(pk(acc.aa, acc.ab), w2); acc.aa = lo(t); acc.ab = hi(t);
     TA = blA ? lo(tt2) : TA; TB = blB ? hi(tt2) : TB;
     lastA = blA ? pos : lastA; lastB = blB ? pos : lastB;
     const float QNAN = __int_as_float(0x7fc00000);           // terminated: the pixel's row coordinate becomes NaN
@@ -280,7 +290,7 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
     float pyfA = inA ? (float)pyA : QNAN, pyfB = inB ? (float)pyB : QNAN;
 
     float TA = 1.f, TB = 1.f;
-    u64 C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f), D2 = bc(0.f), A2 = bc(0.f);
+    FwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t lastA = 0, lastB = 0;
     bool warp_done = __all_sync(0xFFFFFFFFu, !inA && !inB);
 
@@ -306,16 +316,16 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
                     const bool two = bal != 0;
                     const int j1 = two ? __ffs(bal) - 1 : j0;
                     bal &= bal - 1;
-                    FwdFront f0 = fwd_front(rg + j0 * REC_BYTES, pxf, pyfA, pyfB);
-                    FwdFront f1 = fwd_front(rg + j1 * REC_BYTES, pxf, pyfA, pyfB);
-                    if (__any_sync(0xFFFFFFFFu, f0.liveA || f0.liveB))
-                        fwd_back(f0, f0.liveA, f0.liveB, rg + j0 * REC_BYTES, pos0 + j0, TA, TB, C0, C1, C2, D2, A2, lastA, lastB, pyfA, pyfB);
-                    if (two) {
-                        // visit 1's front half saw the row coordinates from before visit 0: drop pixels that just terminated
-                        const bool l1A = f1.liveA && (pyfA == pyfA), l1B = f1.liveB && (pyfB == pyfB);
-                        if (__any_sync(0xFFFFFFFFu, l1A || l1B))
-                            fwd_back(f1, l1A, l1B, rg + j1 * REC_BYTES, pos0 + j1, TA, TB, C0, C1, C2, D2, A2, lastA, lastB, pyfA, pyfB);
-                    }
+                    const FwdFront f0 = fwd_front(rg + j0 * REC_BYTES, pxf, pyfA, pyfB);
+                    const FwdFront f1 = fwd_front(rg + j1 * REC_BYTES, pxf, pyfA, pyfB);
+                    // (no warp vote around the blend: 96 % of the visits have a live lane, and the branch made ptxas copy
+                    // the ten accumulator registers at its join)
+                    fwd_back(f0, fwd_live(lo(f0.p2), lo(f0.al2)), fwd_live(hi(f0.p2), hi(f0.al2)), rg + j0 * REC_BYTES, pos0 + j0,
+                             TA, TB, acc, lastA, lastB, pyfA, pyfB);
+                    // visit 1's front half saw the row coordinates from before visit 0: drop pixels that just terminated
+                    // (`two` false: j1 == j0 and the visit is masked off as a whole)
+                    fwd_back(f1, two && fwd_live(lo(f1.p2), lo(f1.al2)) && (pyfA == pyfA), two && fwd_live(hi(f1.p2), hi(f1.al2)) && (pyfB == pyfB),
+                             rg + j1 * REC_BYTES, pos0 + j1, TA, TB, acc, lastA, lastB, pyfA, pyfB);
                 }
                 if (__all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
             }
@@ -343,21 +353,17 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
         }
         rs.advance(STAGES);
     }
-    const u64 T2 = pk(TA, TB);
-
     const size_t plane = (size_t)va.W * va.H;
     const float bg0 = __ldg(va.bg), bg1 = __ldg(va.bg + 1), bg2 = __ldg(va.bg + 2);
     if (inA) {
         const size_t pix = (size_t)pyA * va.W + px;
-        const float T = lo(T2);
-        out_color[pix] = lo(C0) + T * bg0; out_color[plane + pix] = lo(C1) + T * bg1; out_color[2 * plane + pix] = lo(C2) + T * bg2;
-        out_depth[pix] = lo(D2); out_alpha[pix] = lo(A2); n_contrib[pix] = lastA; final_T[pix] = T;
+        out_color[pix] = acc.c0a + TA * bg0; out_color[plane + pix] = acc.c1a + TA * bg1; out_color[2 * plane + pix] = acc.c2a + TA * bg2;
+        out_depth[pix] = acc.da; out_alpha[pix] = acc.aa; n_contrib[pix] = lastA; final_T[pix] = TA;
     }
     if (inB) {
         const size_t pix = (size_t)pyB * va.W + px;
-        const float T = hi(T2);
-        out_color[pix] = hi(C0) + T * bg0; out_color[plane + pix] = hi(C1) + T * bg1; out_color[2 * plane + pix] = hi(C2) + T * bg2;
-        out_depth[pix] = hi(D2); out_alpha[pix] = hi(A2); n_contrib[pix] = lastB; final_T[pix] = T;
+        out_color[pix] = acc.c0b + TB * bg0; out_color[plane + pix] = acc.c1b + TB * bg1; out_color[2 * plane + pix] = acc.c2b + TB * bg2;
+        out_depth[pix] = acc.db; out_alpha[pix] = acc.ab; n_contrib[pix] = lastB; final_T[pix] = TB;
     }
 }
 
@@ -417,24 +423,21 @@ __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, ui
         float* dst = reinterpret_cast<float*>(sg + __float_as_uint(si.z));
         // pixel = centre + L, d = mean2D - pixel = u - L with u = mean2D - centre
         const float u = si.x - Xc, v = si.y - Yc, o = si.w;
-        // the ten sums of the splat, in SplatGrad float offsets 0,1,2 | 4,5,6,7 | 8,9,10; the parts share the red's
-        const float val[10] = {o * (u * M0 - M1),                                  // sum w dx
-                               o * (v * M0 - My),                                  // sum w dy
-                               Cd,                                                 // dL/ddepth
-                               o * (fmaf(u, fmaf(u, M0, -2.f * M1), M2)),          // sum w dx dx
-                               o * (fmaf(u, fmaf(v, M0, -My), fmaf(-v, M1, Mxy))), // sum w dx dy
-                               o * (fmaf(v, fmaf(v, M0, -2.f * My), Myy)),         // sum w dy dy
-                               M0,                                                 // dL/dopacity (sum G dL/dalpha)
-                               Cr, Cg, Cb};                                        // dL/drgb
-#pragma unroll
-        for (int k = 0; k < (10 + Q::PARTS - 1) / Q::PARTS; k++) {
-            float x = 0.f; int off = -1;
-#pragma unroll
-            for (int q = 0; q < Q::PARTS; q++) {
-                const int vi = k * Q::PARTS + q;
-                if (vi < 10 && part == q) { x = val[vi]; off = vi + (vi >= 3); }
-            }
-            if (off >= 0) atomicAdd(dst + off, x);
+        // the ten sums of the splat = the three float4 of its SplatGrad record; one red.global.add.v4.f32 per float4
+        // (3 vector reds per (quadrant, splat) instead of 10 scalar ones), shared between the parts of the slot
+        const float4 qg = make_float4(o * (u * M0 - M1),                                   // sum w dx
+                                      o * (v * M0 - My),                                   // sum w dy
+                                      Cd, 0.f);                                            // dL/ddepth
+        const float4 qc = make_float4(o * (fmaf(u, fmaf(u, M0, -2.f * M1), M2)),           // sum w dx dx
+                                      o * (fmaf(u, fmaf(v, M0, -My), fmaf(-v, M1, Mxy))),  // sum w dx dy
+                                      o * (fmaf(v, fmaf(v, M0, -2.f * My), Myy)),          // sum w dy dy
+                                      M0);                                                 // dL/dopacity (sum G dL/dalpha)
+        const float4 qk = make_float4(Cr, Cg, Cb, 0.f);                                    // dL/drgb
+        if (Q::PARTS == 2) {
+            red_add_v4(dst + (part == 0 ? 0 : 8), part == 0 ? qg : qk);
+            if (part == 0) red_add_v4(dst + 4, qc);
+        } else {
+            if (part < 3) red_add_v4(dst + 4 * part, part == 0 ? qg : (part == 1 ? qc : qk));
         }
     }
 }
@@ -678,8 +681,8 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     if (use_r1()) return gs_launch_render_backward_r1(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s);
     dim3 grid(va.tiles_x, va.tiles_y);
     static const int stages = env_int("GS_B200_BWD_STAGES", 2);
-    static const int slots = env_int("GS_B200_BWD_SLOTS", 8);
-    static const int occ = env_int("GS_B200_BWD_OCC", 6);
+    static const int slots = env_int("GS_B200_BWD_SLOTS", 16);
+    static const int occ = env_int("GS_B200_BWD_OCC", 4);
 #define BWD(ST, SL, OC)                                                                                                    \
     do {                                                                                                                   \
         static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC>,                        \

@@ -169,16 +169,59 @@ class _Texture(torch.autograd.Function):
         return d_tex, d_uv, None
 
 
+def _mip_pyramid(tex, max_mip_level=None):
+    """2x2 box-filtered levels while both sides are even (1 texel for power-of-two textures), at most max_mip_level."""
+    levels = [tex]
+    while levels[-1].shape[1] % 2 == 0 and levels[-1].shape[2] % 2 == 0 and (max_mip_level is None or len(levels) <= max_mip_level):
+        t = levels[-1]
+        levels.append((0.25 * (t[:, 0::2, 0::2] + t[:, 1::2, 0::2] + t[:, 0::2, 1::2] + t[:, 1::2, 1::2])).contiguous())
+    return levels
+
+
+def _mip_level(uv_da, Ht, Wt, n_levels, mip_level_bias=None):
+    """half log2 of the squared major axis of the pixel footprint in texel units (nvdiffrast calculateMipLevel, restated)."""
+    dsdx, dsdy, dtdx, dtdy = uv_da[..., 0] * Wt, uv_da[..., 1] * Wt, uv_da[..., 2] * Ht, uv_da[..., 3] * Ht
+    A = dsdx * dsdx + dtdx * dtdx
+    Bq = dsdy * dsdy + dtdy * dtdy
+    Cq = dsdx * dsdy + dtdx * dtdy
+    major2 = 0.5 * (A + Bq) + torch.sqrt(0.25 * (A - Bq) * (A - Bq) + Cq * Cq)
+    level = 0.5 * torch.log2(torch.clamp_min(major2, 1e-30))
+    if mip_level_bias is not None:
+        level = level + mip_level_bias
+    return torch.clamp(level, 0.0, float(n_levels - 1))
+
+
 def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode="auto", boundary_mode="wrap", max_mip_level=None):
-    """Bilinear lookup (filter_mode 'linear'; 'auto' resolves to 'linear' — mip-mapped modes are not implemented,
-    the reference's DiffRastRenderer passes filter_mode='linear', diff_mesh_renderer.py:72,105)."""
-    if filter_mode not in ("auto", "linear"):
-        raise NotImplementedError(f"filter_mode={filter_mode!r}: only 'linear' (and 'auto' -> 'linear') is implemented")
+    """filter_mode 'linear': one bilinear lookup (CUDA kernel) — what DiffRastRenderer passes (diff_mesh_renderer.py:72,105).
+    'auto' = 'linear-mipmap-linear' when uv_da or mip_level_bias is given (LGM's texture fit,
+    Gen_3D_Modules/LGM/nerf_marching_cubes_converter.py:229-230), else 'linear'.  The mip-mapped mode runs the same
+    bilinear kernel on every level of a box-filtered pyramid and blends the two levels around the per-pixel level of detail
+    with tent weights; gradients reach the texture (through the pyramid), uv and uv_da."""
+    if filter_mode == "auto":
+        filter_mode = "linear-mipmap-linear" if (uv_da is not None or mip_level_bias is not None) else "linear"
+    if filter_mode not in ("linear", "linear-mipmap-linear"):
+        raise NotImplementedError(f"filter_mode={filter_mode!r}: 'linear' and 'linear-mipmap-linear' (and 'auto') are implemented")
     if boundary_mode not in ("wrap", "clamp"):
         raise NotImplementedError(f"boundary_mode={boundary_mode!r}")
     if tex.dim() != 4 or uv.dim() != 4 or uv.shape[-1] != 2:
         raise ValueError("tex must be [T,Ht,Wt,C], uv must be [B,H,W,2]")
-    return _Texture.apply(tex, uv, 0 if boundary_mode == "wrap" else 1)
+    bmode = 0 if boundary_mode == "wrap" else 1
+    if filter_mode == "linear":
+        return _Texture.apply(tex, uv, bmode)
+    if mip is not None:
+        raise NotImplementedError("pre-built mip stacks (texture_construct_mip) are not implemented")
+    if uv_da is None:
+        uv_da = torch.zeros(*uv.shape[:-1], 4, device=uv.device, dtype=torch.float32)
+    levels = _mip_pyramid(tex.float(), max_mip_level)
+    lod = _mip_level(uv_da.float(), tex.shape[1], tex.shape[2], len(levels), mip_level_bias)
+    out = None
+    for l, t in enumerate(levels):
+        w = torch.clamp(1.0 - (lod - float(l)).abs(), min=0.0)
+        if not bool((w > 0).any()):          # no pixel of this call uses the level
+            continue
+        term = w[..., None] * _Texture.apply(t, uv, bmode)
+        out = term if out is None else out + term
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ antialias

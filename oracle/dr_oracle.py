@@ -160,8 +160,43 @@ def interpolate(attr: torch.Tensor, rast: torch.Tensor, tri: torch.Tensor, rast_
 # --------------------------------------------------------------------------------------------------
 # texture (filter_mode='linear', boundary_mode='wrap')
 # --------------------------------------------------------------------------------------------------
-def texture(tex: torch.Tensor, uv: torch.Tensor, filter_mode="linear", boundary_mode="wrap"):
-    """Bilinear lookup: texel (i,j) centre at ((i+0.5)/W, (j+0.5)/H), row 0 at v=0; wrap (or clamp) addressing."""
+def mip_pyramid(tex: torch.Tensor, max_mip_level=None):
+    """[tex, 2x2 box-filtered halves ...]: levels are added while both sides are even (down to 1 texel for power-of-two
+    textures), at most max_mip_level of them."""
+    levels = [tex]
+    while levels[-1].shape[1] % 2 == 0 and levels[-1].shape[2] % 2 == 0 and (max_mip_level is None or len(levels) <= max_mip_level):
+        t = levels[-1]
+        levels.append(0.25 * (t[:, 0::2, 0::2] + t[:, 1::2, 0::2] + t[:, 0::2, 1::2] + t[:, 1::2, 1::2]))
+    return levels
+
+
+def mip_level(uv_da: torch.Tensor, Ht: int, Wt: int, n_levels: int, mip_level_bias=None):
+    """Level of detail from the screen-space uv derivatives (du/dX, du/dY, dv/dX, dv/dY): half the log2 of the squared
+    major axis of the pixel footprint in texel units (nvdiffrast calculateMipLevel), clamped to the pyramid."""
+    dsdx, dsdy, dtdx, dtdy = uv_da[..., 0] * Wt, uv_da[..., 1] * Wt, uv_da[..., 2] * Ht, uv_da[..., 3] * Ht
+    A = dsdx * dsdx + dtdx * dtdx
+    Bq = dsdy * dsdy + dtdy * dtdy
+    Cq = dsdx * dsdy + dtdx * dtdy
+    major2 = 0.5 * (A + Bq) + torch.sqrt(0.25 * (A - Bq) * (A - Bq) + Cq * Cq)
+    level = 0.5 * torch.log2(torch.clamp_min(major2, 1e-30))
+    if mip_level_bias is not None:
+        level = level + mip_level_bias
+    return torch.clamp(level, 0.0, float(n_levels - 1))
+
+
+def texture(tex: torch.Tensor, uv: torch.Tensor, filter_mode="linear", boundary_mode="wrap", uv_da=None, mip_level_bias=None,
+            max_mip_level=None):
+    """Bilinear lookup: texel (i,j) centre at ((i+0.5)/W, (j+0.5)/H), row 0 at v=0; wrap (or clamp) addressing.
+    'linear-mipmap-linear' (what filter_mode='auto' means when uv_da is given, LGM nerf_marching_cubes_converter.py:230):
+    bilinear in the two pyramid levels around `mip_level`, blended linearly."""
+    if filter_mode == "linear-mipmap-linear":
+        levels = mip_pyramid(tex, max_mip_level)
+        lod = mip_level(uv_da, tex.shape[1], tex.shape[2], len(levels), mip_level_bias)
+        out = 0
+        for l, t in enumerate(levels):
+            w = torch.clamp(1.0 - (lod - float(l)).abs(), min=0.0)              # tent weight = the two-level lerp
+            out = out + w[..., None] * texture(t, uv, "linear", boundary_mode)
+        return out
     assert filter_mode == "linear"
     T, Ht, Wt, C = tex.shape
     B = uv.shape[0]

@@ -586,6 +586,32 @@ def flexi_fixture(out, O):
     out["flexi_mv"] = mv.numpy(); out["flexi_mvp"] = mvp.numpy(); out["flexi_res"] = np.array(res)
     for k, t in outd.items():
         out["flexi_" + k] = t.numpy()
+    # ---- c4 feeding c2: the reference's own FlexiCubes.__call__ (flexicubes.py:133-216 + tables.py, pure torch) extracts
+    # a mesh from a sphere SDF on a 14^3 grid; the reference renderer renders THAT mesh (changing topology is the case
+    # FlexiCubesRenderer exists for).  The GPU test feeds the stored mesh to the CUDA shim.
+    tsrc = open(os.path.join(REF, "MVs_Algorithms/FlexiCubes/tables.py")).read()
+    tables = types.ModuleType("FlexiCubes.tables")
+    exec(compile(tsrc, "ref_flexi_tables", "exec"), tables.__dict__)
+    sys.modules["FlexiCubes.tables"] = tables; mods["FlexiCubes.tables"] = tables
+    fsrc = open(os.path.join(REF, "MVs_Algorithms/FlexiCubes/flexicubes.py")).read().replace("from .tables import *", "from FlexiCubes.tables import *")
+    fns = {}
+    exec(compile(fsrc, "ref_flexicubes", "exec"), fns)
+    fcx = fns["FlexiCubes"](device="cpu")
+    gres = 14
+    x_nx3, cube_fx8 = fcx.construct_voxel_grid(gres)
+    x_nx3 = x_nx3 * 2.0                                                   # grid spans [-1, 1]^3
+    g = torch.Generator().manual_seed(11)
+    sdf = x_nx3.norm(dim=-1) - 0.62 + 0.03 * torch.randn(x_nx3.shape[0], generator=g)      # a bumpy sphere
+    with torch.no_grad():
+        ev, ef, _ = fcx(x_nx3, sdf, cube_fx8, gres, training=False)
+    emesh = util.SimpleMesh(ev.float(), ef.long())
+    emesh.auto_normals()
+    emesh.v_nrm = util.safe_normalize(ev.float())
+    with torch.no_grad():
+        outx = R.render_mesh(emesh, mv, mvp, res, return_types=["mask", "depth", "normal", "vertex_normal"], white_bg=True)
+    out["flexi_ex_v"] = ev.float().numpy(); out["flexi_ex_f"] = ef.numpy().astype(np.int32)
+    for k, t in outx.items():
+        out["flexi_ex_" + k] = t.numpy()
     for k in list(mods):
         sys.modules.pop(k, None)
 

@@ -461,6 +461,10 @@ def test_config1_full_frame_keys_and_sampled_tile_composite_match_the_oracle(dev
     the benchmarked step walks)."""
     from gs_b200 import camera, synthetic
     N, W, H, deg = 1_000_000, 1920, 1080, 3
+    # the oracle's per-tile tensor ops collapse with one thread per core of a 128-core host (bench.py measured 25x slower
+    # than 8 threads): cap the intra-op threads for this test
+    threads0 = torch.get_num_threads()
+    torch.set_num_threads(min(threads0, 16))
     cloud = synthetic.make_cloud("D0", N, deg, seed=0, device=dev)
     cpu = {k: v.cpu() for k, v in cloud.items()}
     vnp = camera.orbit_views(8, W, H)
@@ -541,8 +545,65 @@ def test_config1_full_frame_keys_and_sampled_tile_composite_match_the_oracle(dev
             del fs
     finally:
         R.set_tile_culling(mode0)
+        torch.set_num_threads(threads0)
         out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
         if os.path.isdir(out_dir):
             import json
             with open(os.path.join(out_dir, "config1_parity_stats_%s.json" % "_".join(map(str, view_ids))), "w") as f:
                 json.dump(stats, f, indent=1)
+
+
+# ---------------- other callers of the rasterizer boundary ---------------------------------------------------
+def test_triplane_gaussian_double_render_inside_an_fp32_autocast_region(dev, R):
+    """TriplaneGaussian (Gen_3D_Modules/TriplaneGaussian/models/renderer.py:261-305) calls the rasterizer twice per view
+    inside `torch.autocast(device_type, dtype=torch.float32)` nested in the model's fp16 autocast: once with colours
+    (colors_precomp when cfg.use_rgb), once for the mask with colors_precomp = ones, bg = 0 and sh_degree 0.  Both
+    calls must return fp32 4-tuples that match the oracle, the mask render equals the alpha output, and gradients flow."""
+    N, W, H = 4000, 96, 80
+    cl = O.make_cloud("D1", N, 0, seed=21)
+    st = O.minicam_settings(O.orbit_camera(5, 65, 1.75), W, H, 49.1, sh_degree=0, bg=(0.3, 0.2, 0.1))
+    cols = torch.rand(N, 3, generator=torch.Generator().manual_seed(1))
+    ref_c, _, ref_d, ref_a = O.rasterize(cl["means3D"], None, None, cols, cl["opacities"], cl["scales"], cl["rotations"], None, st)
+    inp = {k: cl[k].to(dev).requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations")}
+    colsd = cols.to(dev).requires_grad_(True)
+    m2 = torch.zeros(N, 3, device=dev, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        junk = torch.mm(torch.ones(4, 4, device=dev), torch.ones(4, 4, device=dev))      # the surrounding model runs in fp16
+        assert junk.dtype == torch.float16
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with torch.autocast(device_type="cuda", dtype=torch.float32):
+                img, radii, depth, alpha = R.GaussianRasterizer(_rs(R, st, dev, 0))(
+                    means3D=inp["means3D"], means2D=m2, shs=None, colors_precomp=colsd, opacities=inp["opacities"],
+                    scales=inp["scales"], rotations=inp["rotations"], cov3D_precomp=None)
+            st0 = O.minicam_settings(O.orbit_camera(5, 65, 1.75), W, H, 49.1, sh_degree=0, bg=(0.0, 0.0, 0.0))
+            with torch.autocast(device_type="cuda", dtype=torch.float32):
+                mask, radii2, depth2, alpha2 = R.GaussianRasterizer(_rs(R, st0, dev, 0))(
+                    means3D=inp["means3D"], means2D=m2, colors_precomp=torch.ones_like(inp["means3D"]), opacities=inp["opacities"],
+                    scales=inp["scales"], rotations=inp["rotations"], cov3D_precomp=None)
+    for t in (img, depth, alpha, mask):
+        assert t.dtype == torch.float32
+    assert float((img.detach().cpu() - ref_c).abs().max()) < RGBA_ATOL
+    assert float((depth.detach().cpu() - ref_d).abs().max()) < RGBA_ATOL and float((alpha.detach().cpu() - ref_a).abs().max()) < RGBA_ATOL
+    assert torch.equal(radii, radii2)
+    assert float((mask - alpha2.expand_as(mask)).abs().max()) < 1e-6                    # ones through the blend = coverage
+    (img.sum() + mask.sum()).backward()
+    assert all(bool(torch.isfinite(v.grad).all()) and float(v.grad.abs().sum()) > 0 for v in inp.values())
+
+
+def test_trellis_supersampled_render_then_antialiased_downsample(dev, R):
+    """TRELLIS (Gen_3D_Modules/TRELLIS/trellis/renderers/gaussian_render.py:211-230): render at resolution * ssaa with
+    overridden colours, then F.interpolate(..., mode='bilinear', antialias=True) down to `resolution`."""
+    import torch.nn.functional as F
+    N, res, ssaa = 5000, 48, 2
+    cl = O.make_cloud("D1", N, 0, seed=33)
+    st = O.minicam_settings(O.orbit_camera(-10, 200, 1.75), res * ssaa, res * ssaa, 40.0, sh_degree=0, bg=(1.0, 1.0, 1.0))
+    cols = torch.rand(N, 3, generator=torch.Generator().manual_seed(2))
+    ref_c, _, _, _ = O.rasterize(cl["means3D"], None, None, cols, cl["opacities"], cl["scales"], cl["rotations"], None, st)
+    ref = F.interpolate(ref_c[None], size=(res, res), mode="bilinear", align_corners=False, antialias=True).squeeze()
+    img, radii, depth, alpha = R.GaussianRasterizer(_rs(R, st, dev, 0))(
+        means3D=cl["means3D"].to(dev), means2D=torch.zeros(N, 3, device=dev), shs=None, colors_precomp=cols.to(dev),
+        opacities=cl["opacities"].to(dev), scales=cl["scales"].to(dev), rotations=cl["rotations"].to(dev), cov3D_precomp=None)
+    got = F.interpolate(img[None], size=(res, res), mode="bilinear", align_corners=False, antialias=True).squeeze()
+    assert got.shape == (3, res, res) and float((got.cpu() - ref).abs().max()) < RGBA_ATOL

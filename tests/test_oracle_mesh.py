@@ -159,3 +159,24 @@ def test_gradients_match_finite_differences_fp64():
         p = tex0.clone(); m = tex0.clone(); p.view(-1)[j] += eps; m.view(-1)[j] -= eps
         fd = (float(render(v, p)) - float(render(v, m))) / (2 * eps)
         assert abs(fd - float(gt.reshape(-1)[j])) <= 1e-5 * max(1.0, abs(fd))
+
+
+def test_mipmapped_texture_levels_and_limits():
+    """'linear-mipmap-linear': zero derivatives -> level 0 = plain bilinear; a footprint of exactly 2^k texels -> level k
+    of the box-filtered pyramid; an anisotropic footprint uses its MAJOR axis; the last level of a power-of-two texture is
+    the mean texel."""
+    g = torch.Generator().manual_seed(0)
+    tex = torch.rand(1, 16, 32, 3, generator=g)
+    uv = torch.rand(1, 5, 7, 2, generator=g)
+    z = torch.zeros(1, 5, 7, 4)
+    assert torch.allclose(D.texture(tex, uv, "linear-mipmap-linear", uv_da=z), D.texture(tex, uv, "linear"))
+    pyr = D.mip_pyramid(tex)
+    assert [tuple(t.shape[1:3]) for t in pyr] == [(16, 32), (8, 16), (4, 8), (2, 4), (1, 2)]
+    assert torch.allclose(pyr[-1].mean(dim=(1, 2)), tex.mean(dim=(1, 2)), atol=1e-6)
+    for k in (1, 2, 3):
+        da = torch.zeros(1, 5, 7, 4)
+        da[..., 0] = (2.0 ** k) / 32          # du/dX = 2^k texels of the 32-wide side, nothing along Y
+        da[..., 3] = 1.0 / 16                 # dv/dY = 1 texel: the major axis decides
+        got = D.texture(tex, uv, "linear-mipmap-linear", uv_da=da)
+        assert torch.allclose(got, D.texture(pyr[k], uv, "linear"), atol=1e-6), k
+    assert float(D.mip_level(torch.full((1, 1, 1, 4), 100.0), 16, 32, len(pyr)).max()) == len(pyr) - 1      # clamped
