@@ -150,7 +150,14 @@ lib.gs_b200_adam_step.restype = _I
 lib.gs_b200_adam_step.argtypes = [_I, _I, _P, _F, _F, _F, _I, _F, _P, _P, _P, _P, _P]
 lib.gs_b200_densify_stats.restype = _I
 lib.gs_b200_densify_stats.argtypes = [_I, _P, _P, _P, _P, _P, _P]
-TRAIN_EXPORTS = ["gs_b200_activate", "gs_b200_adam_step", "gs_b200_densify_stats"]
+lib.gs_b200_densify_scratch_bytes.restype = C.c_size_t
+lib.gs_b200_densify_scratch_bytes.argtypes = [_I]
+lib.gs_b200_densify_plan.restype = _I
+lib.gs_b200_densify_plan.argtypes = [_I, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _P]
+lib.gs_b200_densify_apply.restype = _I
+lib.gs_b200_densify_apply.argtypes = [_I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]
+TRAIN_EXPORTS = ["gs_b200_activate", "gs_b200_adam_step", "gs_b200_densify_stats", "gs_b200_densify_scratch_bytes",
+                 "gs_b200_densify_plan", "gs_b200_densify_apply"]
 
 NSTAGES = 9
 STAGE_NAMES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "composite_fwd",

@@ -62,18 +62,38 @@ class GaussianTrainer:
         return out
 
     def _alloc(self, n):
+        """(Re)binds every per-Gaussian array to n rows.  Storage is grow-only: buffers are allocated for a capacity
+        >= n (1.5x head room once densification starts) and the packed arrays are prefix slices of them, so a
+        densification normally allocates nothing.  Two parameter sets (raw, m1, m2) exist so that the compaction kernel
+        can scatter from one into the other (gs_b200_densify_apply)."""
+        if n > getattr(self, "_cap", 0):
+            cap = n if getattr(self, "_cap", 0) == 0 else max(n, int(1.5 * self._cap))
+            ctot = sum(self._sizes(cap))
+            self._store = [dict(raw=torch.zeros(ctot, device=self.device), m1=torch.zeros(ctot, device=self.device),
+                                m2=torch.zeros(ctot, device=self.device)) for _ in range(2)]
+            self._cur = 0
+            self._aux = dict(act=torch.zeros(8 * cap, device=self.device), grads=torch.zeros(ctot + 3 * cap, device=self.device),
+                             radii=torch.zeros(cap, dtype=torch.int32, device=self.device), accum=torch.zeros(cap, device=self.device),
+                             denom=torch.zeros(cap, device=self.device), maxr=torch.zeros(cap, device=self.device))
+            self._cap = cap
+        self._bind(n, zero=True)
+
+    def _bind(self, n, zero):
         tot = sum(self._sizes(n))
+        st = self._store[self._cur]
         self.N = n
-        self.raw = torch.zeros(tot, device=self.device)
-        self.m1 = torch.zeros(tot, device=self.device); self.m2 = torch.zeros(tot, device=self.device)
+        self.raw, self.m1, self.m2 = st["raw"][:tot], st["m1"][:tot], st["m2"][:tot]
+        if zero:
+            self.raw.zero_(); self.m1.zero_(); self.m2.zero_()
         self.v = self._views(self.raw, n)
-        self.act = torch.zeros(8 * n, device=self.device)                       # activated opac | scales | rots
+        self.act = self._aux["act"][:8 * n]                                     # activated opac | scales | rots
         self.a_opac, self.a_scales, self.a_rots = self.act[:n].view(n, 1), self.act[n:4 * n].view(n, 3), self.act[4 * n:].view(n, 4)
-        self.grads = torch.zeros(tot + 3 * n, device=self.device)               # + means2D
+        self.grads = self._aux["grads"][:tot + 3 * n]                           # + means2D
+        self.grads.zero_()
         self.g_means2D = self.grads[tot:].view(n, 3)
-        self.radii = torch.zeros(n, dtype=torch.int32, device=self.device)
-        self.grad_accum = torch.zeros(n, device=self.device); self.denom = torch.zeros(n, device=self.device)
-        self.max_radii2D = torch.zeros(n, device=self.device)
+        self.radii = self._aux["radii"][:n]; self.radii.zero_()
+        self.grad_accum, self.denom, self.max_radii2D = self._aux["accum"][:n], self._aux["denom"][:n], self._aux["maxr"][:n]
+        self.grad_accum.zero_(); self.denom.zero_(); self.max_radii2D.zero_()
 
     def _init_random(self, n, seed):
         """initialize(None, num_pts) + create_from_pcd (main_3DGS_renderer.py:811-826, 407-433)."""
@@ -217,8 +237,67 @@ class GaussianTrainer:
             if new:
                 self.v[k][k0:] = new[k]
 
-    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, generator=None):
-        """densify_by_clone_and_split + prune (main_3DGS_renderer.py:641-668, 752-781)."""
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, generator=None, normal_samples=None):
+        """densify_by_clone_and_split + prune (main_3DGS_renderer.py:641-668, 752-781).
+        CUDA tensors: stream compaction kernels over the packed buffers (gs_b200_densify_plan / _apply): no boolean-mask
+        indexing, no re-allocation below the capacity, one 40-byte host read for the counts.  `normal_samples`
+        ([2 x split parents, 3] standard normal) replaces the draw of densify_and_split (:653) for replay tests.
+        CPU tensors (fixture tests of the host logic): the torch restatement below."""
+        if self.raw.is_cuda:
+            return self._densify_and_prune_cuda(max_grad, min_opacity, extent, generator, normal_samples)
+        return self._densify_and_prune_torch(max_grad, min_opacity, extent, max_screen_size, generator)
+
+    def _densify_and_prune_cuda(self, max_grad, min_opacity, extent, generator, normal_samples):
+        p, N, dev = self.p, self.N, self.device
+        with torch.cuda.device(dev):
+            work = torch.empty(8 * N, dtype=torch.int32, device=dev)
+            counts = torch.empty(5, dtype=torch.int64, device=dev)
+            scratch = torch.empty(int(_lib.lib.gs_b200_densify_scratch_bytes(N)), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib.gs_b200_densify_plan(N, _ptr(self.v["opacity"]), _ptr(self.v["scaling"]), _ptr(self.grad_accum), _ptr(self.denom),
+                                                     float(max_grad), float(min_opacity), float(extent), float(p.percent_dense),
+                                                     _ptr(work), _ptr(counts), _ptr(scratch), _stream()))
+            n_keep, n_clone, n_sp, n_spk, clone_total = (int(x) for x in counts.cpu())          # the one host sync
+            n_new = n_keep + n_clone + 2 * n_spk
+            if normal_samples is None:
+                z = torch.empty(2 * n_sp, 3, device=dev).normal_(generator=generator) if n_sp else torch.empty(0, 3, device=dev)
+            else:
+                z = normal_samples.to(dev).float().contiguous()
+                assert z.shape == (2 * n_sp, 3), (z.shape, n_sp)
+            src = self._store[self._cur]
+            src_views = (src["raw"][:self.raw.numel()], src["m1"][:self.raw.numel()], src["m2"][:self.raw.numel()])
+            if n_new > self._cap:                # grow-only: both sets move to the new capacity, the live one keeps its contents
+                old_n = self.N
+                self._alloc_grow(n_new)
+                src = self._store[self._cur]
+                tot_old = sum(self._sizes(old_n))
+                src_views = (src["raw"][:tot_old], src["m1"][:tot_old], src["m2"][:tot_old])
+            dst = self._store[1 - self._cur]
+            tot_new = sum(self._sizes(n_new))
+            if n_new > 0:
+                _lib.check(_lib.lib.gs_b200_densify_apply(N, self.M, _ptr(src_views[0]), _ptr(src_views[1]), _ptr(src_views[2]), _ptr(work),
+                                                          n_keep, n_clone, n_sp, n_spk, _ptr(z) if n_sp else None,
+                                                          _ptr(dst["raw"][:max(tot_new, 1)]), _ptr(dst["m1"][:max(tot_new, 1)]),
+                                                          _ptr(dst["m2"][:max(tot_new, 1)]), _stream()))
+            self._cur = 1 - self._cur
+            self._bind(n_new, zero=False)
+        return dict(cloned=clone_total, split=n_sp, pruned=N - n_keep, n=self.N, n_before=N)
+
+    def _alloc_grow(self, n):
+        """capacity growth that keeps the live parameter set (used when a densification outgrows the buffers)."""
+        cap = max(n, int(1.5 * self._cap))
+        ctot = sum(self._sizes(cap))
+        old = self._store
+        self._store = [dict(raw=torch.zeros(ctot, device=self.device), m1=torch.zeros(ctot, device=self.device),
+                            m2=torch.zeros(ctot, device=self.device)) for _ in range(2)]
+        for k in ("raw", "m1", "m2"):
+            self._store[self._cur][k][:old[self._cur][k].numel()].copy_(old[self._cur][k])
+        self._aux = dict(act=torch.zeros(8 * cap, device=self.device), grads=torch.zeros(ctot + 3 * cap, device=self.device),
+                         radii=torch.zeros(cap, dtype=torch.int32, device=self.device), accum=torch.zeros(cap, device=self.device),
+                         denom=torch.zeros(cap, device=self.device), maxr=torch.zeros(cap, device=self.device))
+        self._cap = cap
+
+    def _densify_and_prune_torch(self, max_grad, min_opacity, extent, max_screen_size, generator=None):
+        """The same rules as torch tensor surgery (the host-logic restatement the CPU fixture test pins to the reference)."""
         p = self.p
         grads = self.grad_accum / self.denom
         grads[grads.isnan()] = 0.0

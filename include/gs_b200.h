@@ -260,6 +260,27 @@ int32_t gs_b200_adam_step(int32_t N, int32_t M, const float* lrs6_host, float be
 int32_t gs_b200_densify_stats(int32_t N, const float* dL_dmeans2D, const int32_t* radii, float* xyz_gradient_accum,
                               float* denom, float* max_radii2D, void* stream);
 
+/* ---- densification as stream compaction in the packed layout -----------------------------------------
+ * Replaces GaussianModel.densify_and_prune and the optimizer surgery behind it (main_3DGS_renderer.py:543-688,752-781).
+ * gs_b200_densify_plan: classifies all N Gaussians (clone / split / prune rules of :641-668,752-781 on the raw
+ *   parameters and the statistics of gs_b200_densify_stats) and scans the flags into destination rows.
+ *   work: [8][N] u32 (flags, then offsets); counts_dev: 5 x u64 = survivors, kept clones, split parents, split parents
+ *   whose children are kept, clones selected before the prune; scratch: gs_b200_densify_scratch_bytes(N).
+ *   The caller reads counts_dev (the one host sync), sizes the destination for
+ *   N' = survivors + kept clones + 2 x kept split parents and draws z ~ N(0,1) [2 x split parents, 3] (the draw
+ *   torch.normal(mean=0, std=stds) makes in densify_and_split, :653, before scaling by std).
+ * gs_b200_densify_apply: scatters parameters and both Adam moments from buffers packed for N rows into buffers packed
+ *   for N' rows: survivors in order | kept clones | kept split children (first copies, then second copies); new rows
+ *   get zero moments (cat_tensors_to_optimizer, :606-625); children = R(q/|q|) (exp(scaling) * z) + xyz with scaling
+ *   log(exp(scaling) / 1.6).  Source and destination must not overlap. */
+size_t gs_b200_densify_scratch_bytes(int32_t N);
+int32_t gs_b200_densify_plan(int32_t N, const float* raw_opacity, const float* raw_scaling, const float* grad_accum,
+                             const float* denom, float max_grad, float min_opacity, float extent, float percent_dense,
+                             uint32_t* work, uint64_t* counts_dev, void* scratch, void* stream);
+int32_t gs_b200_densify_apply(int32_t N, int32_t M, const float* src_raw, const float* src_m1, const float* src_m2,
+                              const uint32_t* work, int32_t n_keep, int32_t n_clone, int32_t n_split_parents,
+                              int32_t n_split_keep, const float* z, float* dst_raw, float* dst_m1, float* dst_m2, void* stream);
+
 /* ---- instrumentation (bench.py): kernel-launch counter and per-stage CUDA-event timing ------
  * Stages: 0 preprocess, 1 depth sort, 2 scan, 3 emit, 4 tile sort, 5 ranges, 6 composite fwd,
  *         7 composite bwd, 8 preprocess bwd.  Events are recorded on the stream each stage is

@@ -260,3 +260,67 @@ def test_training_steps_reproduce_the_reference_loop(dev):
             assert float((d > 5e-5).mean()) <= 1e-3 and float(d.max()) <= 2.0 * lrs[k] * (s + 1) + 5e-5, (s, k, float(d.max()))
         moved = max(moved, float(np.abs(G["after_opacity"][s] - G["init_opacity"]).max()))
     assert moved > 0.05                     # the parameters really moved (opacity lr 0.05 per step), this is not 0 == 0
+
+
+def test_cuda_densification_reproduces_the_reference_model_fixture_and_is_fast(dev):
+    """gs_b200_densify_plan / _apply (stream compaction in the packed layout) against tests/golden/ref_training.npz — the
+    state the REFERENCE's GaussianModel.densify_and_prune (main_3DGS_renderer.py:543-688,752-781) left behind on the same
+    inputs, with the same torch.normal draws: parameters, both Adam moments, row order, zeroed statistics.  Then the
+    cost at config-1 scale: a densification of 1M Gaussians (compaction of 3 x 59 floats per row) under 2 ms, with no
+    allocation when the result fits the capacity."""
+    import os
+    from conftest import GOLDEN
+    from gs_b200 import trainer
+    G = np.load(os.path.join(GOLDEN, "ref_training.npz"), allow_pickle=False)
+    N, deg = G["pre_xyz"].shape[0], 1
+    tr = trainer.GaussianTrainer.__new__(trainer.GaussianTrainer)
+    tr.p = trainer.TrainParams(sh_degree=deg); tr.device = dev; tr.M = (deg + 1) ** 2; tr.step_count = 0
+    tr._alloc(N)
+    t = lambda k: torch.from_numpy(G[k]).to(dev)
+    tr.v["xyz"].copy_(t("pre_xyz")); tr.v["opacity"].copy_(t("pre_opacity")); tr.v["scaling"].copy_(t("pre_scaling")); tr.v["rotation"].copy_(t("pre_rotation"))
+    tr.v["shs"].copy_(torch.cat([t("pre_f_dc"), t("pre_f_rest")], dim=1))
+    m1, m2 = tr._views(tr.m1, N), tr._views(tr.m2, N)
+    for k in ("xyz", "opacity", "scaling", "rotation"):
+        m1[k].copy_(t("m1_" + k)); m2[k].copy_(t("m2_" + k))
+    m1["shs"].copy_(torch.cat([t("m1_f_dc"), t("m1_f_rest")], dim=1)); m2["shs"].copy_(torch.cat([t("m2_f_dc"), t("m2_f_rest")], dim=1))
+    tr.grad_accum.copy_(t("grad_accum").squeeze(1)); tr.denom.copy_(t("denom").squeeze(1)); tr.max_radii2D.copy_(t("max_radii2D"))
+    # the reference drew torch.normal(mean=0, std=stds) for [2 x split parents, 3]: the same standard-normal stream, unscaled
+    g = tr.grad_accum / tr.denom; g[g.isnan()] = 0
+    n_split = int(((g >= 2e-4) & (torch.exp(tr.v["scaling"]).max(1).values > 0.01 * 4.0)).sum())
+    torch.manual_seed(int(G["dens_seed"]))
+    z = torch.empty(2 * n_split, 3).normal_()
+    info = tr.densify_and_prune(2e-4, 0.005, 4.0, 1.0, normal_samples=z)
+    assert tr.N == G["dens_xyz"].shape[0] == info["n"] and info["n_before"] == N and info["split"] == n_split
+    ref_shs = np.concatenate([G["dens_f_dc"], G["dens_f_rest"]], axis=1)
+    for mine, ref in (("xyz", G["dens_xyz"]), ("opacity", G["dens_opacity"]), ("scaling", G["dens_scaling"]), ("rotation", G["dens_rotation"]), ("shs", ref_shs)):
+        assert np.allclose(tr.v[mine].cpu().numpy(), ref, rtol=1e-5, atol=1e-6), mine
+    m1, m2 = tr._views(tr.m1, tr.N), tr._views(tr.m2, tr.N)
+    for k in ("xyz", "opacity", "scaling", "rotation"):
+        assert np.array_equal(m1[k].cpu().numpy(), G["dens_m1_" + k]) and np.array_equal(m2[k].cpu().numpy(), G["dens_m2_" + k]), k
+    assert np.array_equal(m1["shs"].cpu().numpy(), np.concatenate([G["dens_m1_f_dc"], G["dens_m1_f_rest"]], axis=1))
+    assert float(tr.grad_accum.abs().max()) == 0 and float(tr.denom.abs().max()) == 0 and float(tr.max_radii2D.abs().max()) == 0
+    # ---- config-1 scale: 1M Gaussians, SH degree 3
+    big = trainer.GaussianTrainer(trainer.TrainParams(num_pts=1_000_000, sh_degree=3), device=dev, seed=0)
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    acc = (torch.rand(big.N, generator=gen) * 4e-4).to(dev)
+    big._alloc_grow(int(1.6 * big.N)); big._bind(big.N, zero=False)          # head room, as after the first growth
+    times = []
+    for it in range(3):
+        n0 = big.N
+        big.grad_accum.copy_(acc[:n0] if acc.numel() >= n0 else torch.rand(n0, device=dev) * 4e-4); big.denom.fill_(1.0)
+        big.v["opacity"][: n0 // 20] = -8.0                                    # 5 % pruned
+        cap0 = big._cap
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        info = big.densify_and_prune(2e-4, 0.005, 4.0, 1.0)
+        e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        assert info["cloned"] > 1000 and info["pruned"] >= n0 // 20 and big.N == info["n"]
+        if big._cap == cap0 and it > 0:
+            assert times[-1] < 2.0, times
+        acc = torch.rand(big.N, generator=gen).to(dev) * 4e-4
+    log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(log_dir):
+        import json
+        json.dump({"densify_ms_at_1M": times, "n_after": big.N}, open(os.path.join(log_dir, "densify_timing.json"), "w"))
