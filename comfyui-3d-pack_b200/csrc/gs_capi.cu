@@ -497,7 +497,16 @@ struct StepCache {
         return 0;
     }
 };
-thread_local StepCache g_step;
+// one pipeline state per (thread, device): streams, events and workspaces belong to the device that was current when
+// they were created, so a thread that drives a second GPU gets a second set instead of launching onto the first one's
+StepCache& step_cache() {
+    thread_local std::unique_ptr<StepCache> caches[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!caches[dev]) caches[dev].reset(new StepCache());
+    return *caches[dev];
+}
 struct UserSink { gs_b200_grad_sink fn = nullptr; void* user = nullptr; int nchunks = 1; };
 thread_local UserSink g_user_sink;
 
@@ -526,7 +535,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
               const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
               const cudaEvent_t* up_ready, const PackedPtrs& grd, float* images_dev, int64_t* num_rendered_out,
               cudaStream_t user, const GradSink* sink = nullptr, const StepOpts* opts = nullptr) {
-    StepCache& C = g_step;
+    StepCache& C = step_cache();
     if (C.busy) { gs_set_error("step: re-entrant call from a view hook (the per-thread pipeline state is in use)"); return 1; }
     struct BusyGuard { bool& b; explicit BusyGuard(bool& x) : b(x) { b = true; } ~BusyGuard() { b = false; } } busy_guard(C.busy);
     const StepOpts defaults;
@@ -682,7 +691,7 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     cudaStream_t s = (cudaStream_t)stream_;
     if (V <= 0 || N <= 0 || !views_host || !means3D_host || !shs_host || !opacities_host || !scales_host ||
         !rotations_host || !dL_dout_host || (!grads_host && !grads_dev)) { gs_set_error("step_host: bad argument"); return 1; }
-    StepCache& C = g_step;
+    StepCache& C = step_cache();
     if (C.ensure_init()) return 1;
     const size_t npix = (size_t)H * W;
     const size_t n_par = (size_t)N * (3 + 3 * (size_t)M + 1 + 3 + 4);
@@ -794,7 +803,7 @@ struct TrainLossCtx {
 int32_t train_loss_hook(void* user, int32_t v, void* stream_) {
     TrainLossCtx* q = (TrainLossCtx*)user;
     cudaStream_t s = (cudaStream_t)stream_;
-    StepCache& C = g_step;
+    StepCache& C = step_cache();
     Slot* S = (s == C.slot[0].stream) ? &C.slot[0] : &C.slot[1];
     if (Slot::ensure(S->loss_ws, gs_image_loss_scratch_bytes(q->H, q->W), s)) return 1;
     const size_t npix = (size_t)q->H * q->W;

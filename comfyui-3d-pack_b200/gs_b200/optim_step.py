@@ -105,11 +105,12 @@ def step_device_pipelined(params: PackedParams, views: ViewSet, dL_dout: torch.T
     import numpy as np
     assert views.host.dtype == np.float32 and views.host.flags["C_CONTIGUOUS"]
     pairs = C.c_int64(0)
-    _lib.check(_lib.lib.gs_b200_step_device(
-        views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
-        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
-        _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads),
-        None if out_images is None else _ptr(out_images), C.byref(pairs), _stream()))
+    with torch.cuda.device(params.means3D.device):        # the pipeline state is per device (streams, workspaces)
+        _lib.check(_lib.lib.gs_b200_step_device(
+            views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
+            _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+            _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads),
+            None if out_images is None else _ptr(out_images), C.byref(pairs), _stream()))
     return int(pairs.value)
 
 
@@ -137,11 +138,12 @@ def step_device_loss(params: PackedParams, views: ViewSet, loss_grad_fn, images:
             return 1
     cb = _lib.VIEW_HOOK(_hook)
     pairs = C.c_int64(0)
-    rc = _lib.lib.gs_b200_step_device_hook(
-        views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
-        _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
-        _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads), _ptr(images),
-        None if radii is None else _ptr(radii), cb, None, C.byref(pairs), _stream())
+    with torch.cuda.device(params.means3D.device):
+        rc = _lib.lib.gs_b200_step_device_hook(
+            views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
+            _ptr(views.dev), params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities),
+            _ptr(params.scales), _ptr(params.rotations), _ptr(dL_dout), _ptr(params.grads), _ptr(images),
+            None if radii is None else _ptr(radii), cb, None, C.byref(pairs), _stream())
     if err:
         raise err[0]
     _lib.check(rc)
@@ -174,7 +176,8 @@ def step_device_train(params: PackedParams, views: ViewSet, ref_images: torch.Te
     if radii is not None:
         assert radii.dtype == torch.int32 and radii.shape == (V, params.N) and radii.is_contiguous()
     pairs = C.c_int64(0)
-    _lib.check(_lib.lib.gs_b200_step_device_train(
+    with torch.cuda.device(params.means3D.device):
+      _lib.check(_lib.lib.gs_b200_step_device_train(
         V, H, W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data), _ptr(views.dev),
         params.N, params.M, _ptr(params.means3D), _ptr(params.shs), _ptr(params.opacities), _ptr(params.scales),
         _ptr(params.rotations), _ptr(ref_images), _ptr(ref_masks), float(lambda_ssim), float(lambda_alpha), float(loss_scale),
@@ -196,7 +199,8 @@ def render_views(params: PackedParams, views: ViewSet, images: torch.Tensor = No
     if radii is not None:
         assert radii.dtype == torch.int32 and radii.shape == (views.V, params.N) and radii.is_contiguous()
     pairs = C.c_int64(0)
-    _lib.check(_lib.lib.gs_b200_render_views(
+    with torch.cuda.device(params.means3D.device):
+      _lib.check(_lib.lib.gs_b200_render_views(
         views.V, views.H, views.W, views.sh_degree, float(views.scale_modifier), C.c_void_p(views.host.ctypes.data),
         _ptr(views.dev), params.N, params.M, _ptr(params.means3D), None if colors_precomp is not None else _ptr(params.shs),
         None if colors_precomp is None else _ptr(colors_precomp.contiguous().float()), _ptr(params.opacities),

@@ -131,8 +131,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.state = state
         ctx.bufs = bufs
         ctx.view_keep = keep
-        ctx.inputs = (m3, sh_, cp_, op_, sc_, ro_, cv_)
-        ctx.radii = radii
+        # save_for_backward (not plain attributes): an in-place update of a parameter between forward and backward then
+        # trips autograd's version check instead of silently pairing new parameters with the saved binning state
+        ctx.save_for_backward(m3, sh_, cp_, op_, sc_, ro_, cv_, radii)
         ctx.M = M
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha
@@ -140,7 +141,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_color, g_radii, g_depth, g_alpha):
         rs = ctx.rs
-        m3, sh_, cp_, op_, sc_, ro_, cv_ = ctx.inputs
+        m3, sh_, cp_, op_, sc_, ro_, cv_, radii = ctx.saved_tensors
         dev = m3.device
         N = m3.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
@@ -161,7 +162,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             bufs = _Buffers(dev)
             rc = _lib.lib.gs_b200_rasterize_backward(
                 C.byref(view), N, ctx.M, _ptr(m3), _ptr(sh_), _ptr(cp_), _ptr(op_), _ptr(sc_), _ptr(ro_), _ptr(cv_),
-                _ptr(ctx.radii), C.byref(ctx.state), _ptr(gc), _ptr(gd), _ptr(ga),
+                _ptr(radii), C.byref(ctx.state), _ptr(gc), _ptr(gd), _ptr(ga),
                 _ptr(d_m3), _ptr(d_m2), _ptr(d_sh), _ptr(d_cp), _ptr(d_op), _ptr(d_sc), _ptr(d_ro), _ptr(d_cv),
                 0, bufs.cb, None, _stream())
             bufs.scratch.clear()
@@ -218,6 +219,9 @@ def forward_with_state(raster_settings, means3D, opacities, shs=None, colors_pre
     class _Ctx:
         def mark_non_differentiable(self, *a):
             pass
+
+        def save_for_backward(self, *a):
+            self.saved_tensors = a
     ctx = _Ctx()
     color, radii, depth, alpha = _RasterizeGaussians.forward(
         ctx, means3D, None, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, raster_settings)

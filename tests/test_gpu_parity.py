@@ -607,3 +607,20 @@ def test_trellis_supersampled_render_then_antialiased_downsample(dev, R):
         opacities=cl["opacities"].to(dev), scales=cl["scales"].to(dev), rotations=cl["rotations"].to(dev), cov3D_precomp=None)
     got = F.interpolate(img[None], size=(res, res), mode="bilinear", align_corners=False, antialias=True).squeeze()
     assert got.shape == (3, res, res) and float((got.cpu() - ref).abs().max()) < RGBA_ATOL
+
+
+def test_in_place_parameter_update_before_backward_is_detected(dev, R):
+    """The autograd node saves its tensor inputs with save_for_backward: an optimizer.step()-style in-place update between
+    forward and a retained backward raises autograd's version error instead of returning gradients that pair the new
+    parameters with the old binning state."""
+    N, W, H = 500, 48, 48
+    cl = O.make_cloud("D1", N, 0, seed=9)
+    st = O.minicam_settings(O.orbit_camera(0, 0, 1.75), W, H, 49.1, sh_degree=0)
+    inp = {k: cl[k].to(dev).requires_grad_(True) for k in NAMES}
+    img, _, _, _ = R.GaussianRasterizer(_rs(R, st, dev, 0))(means3D=inp["means3D"], means2D=torch.zeros(N, 3, device=dev), shs=inp["shs"],
+                                                             colors_precomp=None, opacities=inp["opacities"], scales=inp["scales"],
+                                                             rotations=inp["rotations"], cov3D_precomp=None)
+    with torch.no_grad():
+        inp["means3D"].add_(0.01)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        img.sum().backward()
