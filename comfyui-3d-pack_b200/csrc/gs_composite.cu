@@ -493,7 +493,7 @@ __device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
 }
 
-template <int STAGES, int SLOTS, int MINB>
+template <int STAGES, int SLOTS, int MINB, bool VOTE>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                           const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
@@ -593,12 +593,12 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                     bal &= ~(1u << j1);
                     const BwdFront f0 = bwd_front(rg + j0 * REC_BYTES, pos0 + j0, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
-                    if (__any_sync(0xFFFFFFFFu, f0.any)) {
+                    if (!VOTE || __any_sync(0xFFFFFFFFu, f0.any)) {
                         bwd_back(f0, T2, behind, qwG + nq * 8, qwD + nq * 8);
                         if (lane == 0) put_slot(slot_base + nq * 16, f0, ld_volatile_s32(ig + j0 * 4));
                         if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
                     }
-                    if (two && __any_sync(0xFFFFFFFFu, f1.any)) {
+                    if (two && (!VOTE || __any_sync(0xFFFFFFFFu, f1.any))) {
                         bwd_back(f1, T2, behind, qwG + nq * 8, qwD + nq * 8);
                         if (lane == 0) put_slot(slot_base + nq * 16, f1, ld_volatile_s32(ig + j1 * 4));
                         if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
@@ -685,13 +685,19 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     static const int occ = env_int("GS_B200_BWD_OCC", 4);
 #define BWD(ST, SL, OC)                                                                                                    \
     do {                                                                                                                   \
-        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC>,                        \
+        if (vote) BWD_(ST, SL, OC, true); else BWD_(ST, SL, OC, false);                                                    \
+    } while (0)
+#define BWD_(ST, SL, OC, VT)                                                                                               \
+    do {                                                                                                                   \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC, VT>,                    \
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, SL)); \
         GS_CUDA_CHECK(attr);                                                                                               \
-        composite_backward_kernel<ST, SL, OC><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+        composite_backward_kernel<ST, SL, OC, VT><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
+    static const bool vote = env_int("GS_B200_BWD_VOTE", 1) != 0;
     if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
     else             { if (stages == 3) BWD(3, 8, 5); else if (occ >= 6) BWD(2, 8, 6); else if (occ == 5) BWD(2, 8, 5); else BWD(2, 8, 4); }
+#undef BWD_
 #undef BWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());

@@ -5,10 +5,11 @@
 // the reference builds boolean masks, rebuilds every nn.Parameter and patches the Adam state dicts.  Here
 //   plan : one pass classifies every Gaussian (clone / split / keep, and whether its children survive the prune), four
 //          exclusive scans turn the flags into destination rows; the host reads the four counts (the only sync, 32 B);
-//   apply: one pass scatters parameters AND both Adam moments from the source buffers into destination buffers laid
-//          out for the new N — survivors in order, then the kept clones, then the kept split children (first copies,
-//          then second copies: the order torch.cat / repeat(2, 1) / mask produce in the reference) — new rows with zero
-//          moments (cat_tensors_to_optimizer, :606-625).
+//   apply: a destination map (source row + kind per new row) is scattered once, then every group of the parameters
+//          AND of both Adam moments is gathered through it into buffers laid out for the new N, fully coalesced on the
+//          writing side — survivors in order, then the kept clones, then the kept split children (first copies, then
+//          second copies: the order torch.cat / repeat(2, 1) / mask produce in the reference) — new rows with zero
+//          moments (cat_tensors_to_optimizer, :606-625); a last small kernel samples the children.
 // Order of the rules (reproduced, pinned by tests/golden/ref_training.npz):  grads = accum / denom, NaN -> 0;
 // clone = grads >= thr and max(exp(scaling)) <= percent_dense * extent; split = the same with >;  split uses
 // samples = N(0, exp(scaling)) rotated by the normalised quaternion, new scaling = log(exp(scaling) / (0.8 * 2));
@@ -62,70 +63,61 @@ __host__ __device__ inline Groups groups_of(size_t n, size_t M) {
     return g;
 }
 
-// one warp per source Gaussian: lanes copy the SH row (3M floats), lanes 0..10 the 11 small-group floats
-__device__ __forceinline__ void copy_row(const float* __restrict__ src, float* __restrict__ dst, const Groups& gs, const Groups& gd,
-                                         size_t i, size_t d, int M, int lane, bool zero) {
-    const int row = 3 * M;
-    for (int k = lane; k < row; k += 32) dst[gd.shs + d * row + k] = zero ? 0.f : src[gs.shs + i * row + k];
-    if (lane < 3) dst[gd.xyz + 3 * d + lane] = zero ? 0.f : src[gs.xyz + 3 * i + lane];
-    else if (lane == 3) dst[gd.opac + d] = zero ? 0.f : src[gs.opac + i];
-    else if (lane < 7) dst[gd.scal + 3 * d + (lane - 4)] = zero ? 0.f : src[gs.scal + 3 * i + (lane - 4)];
-    else if (lane < 11) dst[gd.rot + 4 * d + (lane - 7)] = zero ? 0.f : src[gs.rot + 4 * i + (lane - 7)];
-}
+// Destination map: for every row of the new packing its source row and what it is (bit 31: new row = zero Adam
+// moments; bits 30..29: 0 survivor / clone, 1 first child, 2 second child of a split parent).
+constexpr uint32_t MAP_NEW = 0x80000000u, MAP_CHILD_SHIFT = 29, MAP_ROW_MASK = 0x1FFFFFFFu;
 
 __global__ void __launch_bounds__(DN_THREADS)
-densify_apply_kernel(int N, int M, const float* __restrict__ src_raw, const float* __restrict__ src_m1,
-                     const float* __restrict__ src_m2, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offs,
-                     int n_keep, int n_clone, int n_split_parents, int n_split_keep, const float* __restrict__ z,
-                     float* __restrict__ dst_raw, float* __restrict__ dst_m1, float* __restrict__ dst_m2) {
-    const int lane = threadIdx.x & 31;
-    const size_t nnew = (size_t)n_keep + n_clone + 2 * (size_t)n_split_keep;
-    const Groups gs = groups_of((size_t)N, (size_t)M), gd = groups_of(nnew, (size_t)M);
-    for (int i = blockIdx.x * (DN_THREADS / 32) + (threadIdx.x >> 5); i < N; i += gridDim.x * (DN_THREADS / 32)) {
-        const uint32_t f0 = flags[i], f1 = flags[(size_t)N + i], f3 = flags[3 * (size_t)N + i];
-        if (f0) {                                   // survivor: parameters and moments move together
-            const size_t d = offs[i];
-            copy_row(src_raw, dst_raw, gs, gd, i, d, M, lane, false);
-            copy_row(src_m1, dst_m1, gs, gd, i, d, M, lane, false);
-            copy_row(src_m2, dst_m2, gs, gd, i, d, M, lane, false);
-        }
-        if (f1) {                                   // clone: same parameters, zero Adam state
-            const size_t d = (size_t)n_keep + offs[(size_t)N + i];
-            copy_row(src_raw, dst_raw, gs, gd, i, d, M, lane, false);
-            copy_row(src_m1, dst_m1, gs, gd, i, d, M, lane, true);
-            copy_row(src_m2, dst_m2, gs, gd, i, d, M, lane, true);
-        }
-        if (f3) {                                   // two children sampled inside the parent
-            const size_t pr = offs[2 * (size_t)N + i], r = offs[3 * (size_t)N + i];
-            const float* q = src_raw + gs.rot + 4 * (size_t)i;
-            float qr = q[0], qx = q[1], qy = q[2], qz = q[3];
-            const float inv = 1.0f / sqrtf(qr * qr + qx * qx + qy * qy + qz * qz);       // build_rotation normalises (:81-102)
-            qr *= inv; qx *= inv; qy *= inv; qz *= inv;
-            const float R[9] = {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - qr * qz), 2.f * (qx * qz + qr * qy),
-                                2.f * (qx * qy + qr * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - qr * qx),
-                                2.f * (qx * qz - qr * qy), 2.f * (qy * qz + qr * qx), 1.f - 2.f * (qx * qx + qy * qy)};
-            const float s0 = expf(src_raw[gs.scal + 3 * (size_t)i]), s1 = expf(src_raw[gs.scal + 3 * (size_t)i + 1]),
-                        s2 = expf(src_raw[gs.scal + 3 * (size_t)i + 2]);
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const size_t d = (size_t)n_keep + n_clone + (size_t)c * n_split_keep + r;
-                copy_row(src_raw, dst_raw, gs, gd, i, d, M, lane, false);      // shs, opacity, rotation stay; xyz / scaling overwritten below
-                copy_row(src_m1, dst_m1, gs, gd, i, d, M, lane, true);
-                copy_row(src_m2, dst_m2, gs, gd, i, d, M, lane, true);
-                __syncwarp();
-                const float* zz = z + 3 * ((size_t)c * n_split_parents + pr);
-                const float e0 = s0 * zz[0], e1 = s1 * zz[1], e2 = s2 * zz[2];         // torch.normal(0, std) = std * z
-                if (lane < 3) {
-                    const float o0 = R[0] * e0 + R[1] * e1 + R[2] * e2, o1 = R[3] * e0 + R[4] * e1 + R[5] * e2,
-                                o2 = R[6] * e0 + R[7] * e1 + R[8] * e2;                                        // bmm(R, samples)
-                    const float off = lane == 0 ? o0 : (lane == 1 ? o1 : o2);
-                    dst_raw[gd.xyz + 3 * d + lane] = off + src_raw[gs.xyz + 3 * (size_t)i + lane];
-                    const float sl = lane == 0 ? s0 : (lane == 1 ? s1 : s2);
-                    dst_raw[gd.scal + 3 * d + lane] = logf(sl / (0.8f * 2.f));
-                }
-            }
-        }
+densify_map_kernel(int N, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offs, int n_keep, int n_clone,
+                   int n_split_keep, uint32_t* __restrict__ dst_map, uint32_t* __restrict__ child_rank) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    if (flags[i]) dst_map[offs[i]] = (uint32_t)i;
+    if (flags[(size_t)N + i]) dst_map[(size_t)n_keep + offs[(size_t)N + i]] = (uint32_t)i | MAP_NEW;
+    if (flags[3 * (size_t)N + i]) {
+        const size_t r = offs[3 * (size_t)N + i];
+        const size_t d0 = (size_t)n_keep + n_clone + r, d1 = d0 + n_split_keep;
+        dst_map[d0] = (uint32_t)i | MAP_NEW | (1u << MAP_CHILD_SHIFT);
+        dst_map[d1] = (uint32_t)i | MAP_NEW | (2u << MAP_CHILD_SHIFT);
+        child_rank[r] = offs[2 * (size_t)N + i];            // rank of the parent among ALL split parents: row of its z samples
     }
+}
+
+// one thread per float of the destination group: coalesced writes, reads in long ascending runs
+__global__ void __launch_bounds__(DN_THREADS)
+densify_gather_kernel(size_t total, int width, const uint32_t* __restrict__ dst_map, const float* __restrict__ src,
+                      float* __restrict__ dst, int zero_new) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const size_t d = e / (size_t)width;
+    const int k = (int)(e - d * (size_t)width);
+    const uint32_t m = dst_map[d];
+    dst[e] = (zero_new && (m & MAP_NEW)) ? 0.f : src[(size_t)(m & MAP_ROW_MASK) * width + k];
+}
+
+// split children: xyz = R(q/|q|) (exp(scaling) * z) + xyz ; scaling = log(exp(scaling) / 1.6)   (densify_and_split, :641-668)
+__global__ void __launch_bounds__(DN_THREADS)
+densify_children_kernel(int n_children, int n_split_keep, int n_split_parents, size_t first_row, const uint32_t* __restrict__ dst_map,
+                        const uint32_t* __restrict__ child_rank, const float* __restrict__ src_xyz, const float* __restrict__ src_scal,
+                        const float* __restrict__ src_rot, const float* __restrict__ z, float* __restrict__ dst_xyz,
+                        float* __restrict__ dst_scal) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_children) return;
+    const size_t d = first_row + j;
+    const uint32_t m = dst_map[d];
+    const size_t i = m & MAP_ROW_MASK;
+    const int c = (int)((m >> MAP_CHILD_SHIFT) & 3u) - 1;
+    const int r = j - c * n_split_keep;
+    float qr = src_rot[4 * i], qx = src_rot[4 * i + 1], qy = src_rot[4 * i + 2], qz = src_rot[4 * i + 3];
+    const float inv = 1.0f / sqrtf(qr * qr + qx * qx + qy * qy + qz * qz);       // build_rotation normalises (:81-102)
+    qr *= inv; qx *= inv; qy *= inv; qz *= inv;
+    const float s0 = expf(src_scal[3 * i]), s1 = expf(src_scal[3 * i + 1]), s2 = expf(src_scal[3 * i + 2]);
+    const float* zz = z + 3 * ((size_t)c * n_split_parents + child_rank[r]);
+    const float e0 = s0 * zz[0], e1 = s1 * zz[1], e2 = s2 * zz[2];               // torch.normal(0, std) = std * z
+    dst_xyz[3 * d + 0] = (1.f - 2.f * (qy * qy + qz * qz)) * e0 + (2.f * (qx * qy - qr * qz)) * e1 + (2.f * (qx * qz + qr * qy)) * e2 + src_xyz[3 * i + 0];
+    dst_xyz[3 * d + 1] = (2.f * (qx * qy + qr * qz)) * e0 + (1.f - 2.f * (qx * qx + qz * qz)) * e1 + (2.f * (qy * qz - qr * qx)) * e2 + src_xyz[3 * i + 1];
+    dst_xyz[3 * d + 2] = (2.f * (qx * qz - qr * qy)) * e0 + (2.f * (qy * qz + qr * qx)) * e1 + (1.f - 2.f * (qx * qx + qy * qy)) * e2 + src_xyz[3 * i + 2];
+    dst_scal[3 * d + 0] = logf(s0 / (0.8f * 2.f)); dst_scal[3 * d + 1] = logf(s1 / (0.8f * 2.f)); dst_scal[3 * d + 2] = logf(s2 / (0.8f * 2.f));
 }
 
 }  // namespace
@@ -160,12 +152,39 @@ int32_t gs_b200_densify_apply(int32_t N, int32_t M, const float* src_raw, const 
     cudaStream_t s = (cudaStream_t)stream_;
     if (N <= 0 || M <= 0 || !src_raw || !src_m1 || !src_m2 || !work || !dst_raw || !dst_m1 || !dst_m2 || (n_split_keep > 0 && !z) ||
         n_keep < 0 || n_clone < 0 || n_split_parents < n_split_keep || n_split_keep < 0) { gs_set_error("densify_apply: bad argument"); return 1; }
-    const int warps_per_block = DN_THREADS / 32;
-    const int blocks = std::min((N + warps_per_block - 1) / warps_per_block, 148 * 32);
-    densify_apply_kernel<<<blocks, DN_THREADS, 0, s>>>(N, M, src_raw, src_m1, src_m2, work, work + 4 * (size_t)N, n_keep, n_clone,
-                                                       n_split_parents, n_split_keep, z, dst_raw, dst_m1, dst_m2);
-    gs_count_launches(1);
+    const size_t nnew = (size_t)n_keep + n_clone + 2 * (size_t)n_split_keep;
+    if (nnew == 0) return 0;
+    if (nnew > MAP_ROW_MASK || (size_t)N > MAP_ROW_MASK) { gs_set_error("densify_apply: more than 2^29 rows"); return 1; }
+    // the destination map and the child ranks live in the flag / offset workspace's tail?  No: they must not alias the
+    // flags and offsets the map kernel reads -> a stream-ordered scratch allocation
+    uint32_t* dst_map = nullptr;
+    GS_CUDA_CHECK(cudaMallocAsync((void**)&dst_map, (nnew + (size_t)std::max(n_split_keep, 1)) * sizeof(uint32_t), s));
+    uint32_t* child_rank = dst_map + nnew;
+    densify_map_kernel<<<(N + DN_THREADS - 1) / DN_THREADS, DN_THREADS, 0, s>>>(N, work, work + 4 * (size_t)N, n_keep, n_clone, n_split_keep,
+                                                                               dst_map, child_rank);
+    const Groups gs = groups_of((size_t)N, (size_t)M), gd = groups_of(nnew, (size_t)M);
+    const size_t so[5] = {gs.xyz, gs.shs, gs.opac, gs.scal, gs.rot}, dofs[5] = {gd.xyz, gd.shs, gd.opac, gd.scal, gd.rot};
+    const int width[5] = {3, 3 * M, 1, 3, 4};
+    const float* srcs[3] = {src_raw, src_m1, src_m2};
+    float* dsts[3] = {dst_raw, dst_m1, dst_m2};
+    int launches = 1;
+    for (int b = 0; b < 3; b++)
+        for (int g = 0; g < 5; g++) {
+            const size_t total = nnew * (size_t)width[g];
+            densify_gather_kernel<<<(unsigned)((total + DN_THREADS - 1) / DN_THREADS), DN_THREADS, 0, s>>>(
+                total, width[g], dst_map, srcs[b] + so[g], dsts[b] + dofs[g], b > 0 ? 1 : 0);
+            launches++;
+        }
+    if (n_split_keep > 0) {
+        const int nc = 2 * n_split_keep;
+        densify_children_kernel<<<(nc + DN_THREADS - 1) / DN_THREADS, DN_THREADS, 0, s>>>(
+            nc, n_split_keep, n_split_parents, (size_t)n_keep + n_clone, dst_map, child_rank, src_raw + gs.xyz, src_raw + gs.scal,
+            src_raw + gs.rot, z, dst_raw + gd.xyz, dst_raw + gd.scal);
+        launches++;
+    }
+    gs_count_launches(launches);
     GS_CUDA_CHECK(cudaGetLastError());
+    GS_CUDA_CHECK(cudaFreeAsync(dst_map, s));
     return 0;
 }
 

@@ -317,7 +317,7 @@ def test_cuda_densification_reproduces_the_reference_model_fixture_and_is_fast(d
         e1.record(); torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
         assert info["cloned"] > 1000 and info["pruned"] >= n0 // 20 and big.N == info["n"]
-        if big._cap == cap0 and it > 0:
+        if big._cap == cap0:                      # no capacity growth in this densification: nothing was allocated
             assert times[-1] < 2.0, times
         acc = torch.rand(big.N, generator=gen).to(dev) * 4e-4
     log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
