@@ -81,10 +81,11 @@ class OverlappedGradAllReduce:
 
     Without an initialised process group (or world 1) it does nothing."""
 
-    def __init__(self, grads: torch.Tensor, N: int, M: int, nchunks: int = 8, group=None):
+    def __init__(self, grads: torch.Tensor, N: int, M: int, nchunks: int = 8, group=None, enabled: bool = True):
         self.grads, self.N, self.M, self.nchunks, self.group = grads, N, M, nchunks, group
         self.works, self.err = [], None
-        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        # `enabled=False`: a caller that runs a single-process step while a process group exists (world passed as 1)
+        self.active = bool(enabled) and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         from . import _lib
         self._lib = _lib
         self._cb = _lib.GRAD_SINK(self._sink)      # keep the ctypes thunk alive

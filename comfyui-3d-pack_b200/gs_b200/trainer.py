@@ -165,7 +165,7 @@ class GaussianTrainer:
         per_view = torch.zeros(V, device=self.device)
         # data parallel: the all-reduce of the packed gradients is issued in Gaussian-range chunks from inside the step,
         # behind its last pass (parallel.OverlappedGradAllReduce); inactive without a process group
-        ar = parallel.OverlappedGradAllReduce(self.grads, self.N, self.M, nchunks=8)
+        ar = parallel.OverlappedGradAllReduce(self.grads, self.N, self.M, nchunks=8, enabled=world > 1)
         ar.__enter__()
         try:
             self._run_views(views_np, W, H, ref_images, ref_masks, world, total, per_view, loss_fn)
@@ -175,7 +175,6 @@ class GaussianTrainer:
         if world > 1:
             if ar.active:
                 ar.wait()
-            if torch.distributed.is_initialized():
                 torch.distributed.all_reduce(loss_sum)
         self._optimise(world, loss_sum)
         return float(loss_sum) / world
@@ -217,7 +216,8 @@ class GaussianTrainer:
             _lib.check(_lib.lib.gs_b200_densify_stats(self.N, _ptr(self.g_means2D), _ptr(self.radii), _ptr(self.grad_accum),
                                                       _ptr(self.denom), _ptr(self.max_radii2D), _stream()))
             if s % p.densification_interval == 0:
-                parallel.allreduce_densify_stats(self.grad_accum, self.denom, self.max_radii2D)
+                if world > 1:
+                    parallel.allreduce_densify_stats(self.grad_accum, self.denom, self.max_radii2D)
                 self.densify_and_prune(p.densify_grad_threshold, 0.005, 4.0, 1.0)
             if s % p.opacity_reset_interval == 0:
                 self.reset_opacity()

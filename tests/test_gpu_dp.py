@@ -134,9 +134,16 @@ def test_two_rank_nccl_step_and_trainer_match_the_single_process_run():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=900)
+    try:
+        out = q.get(timeout=420)
+    except Exception:  # noqa: BLE001  (a rank hung or died: do not leave NCCL kernels spinning on the GPUs)
+        for p in procs:
+            p.kill()
+        raise
     for p in procs:
-        p.join(timeout=300)
+        p.join(timeout=120)
+        if p.is_alive():
+            p.kill()
     assert "error" not in out, out.get("error")
     log_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(log_dir):
