@@ -70,9 +70,9 @@ def chunk_slices(N: int, M: int, first: int, count: int):
 
 class OverlappedGradAllReduce:
     """One logical all-reduce of the packed gradient buffer per step, issued in Gaussian-range chunks from inside the
-    step: the library calls back after each range of its last pass has been enqueued, and the range's six slices are
-    all-reduced on NCCL's stream (ordered after that kernel) while the next range is computed.  Only the last chunk's
-    collective is exposed.
+    step: the library calls back after each range of its last pass has been enqueued, and the range's rows of the SH
+    gradient block (77 % of the buffer) are all-reduced on NCCL's stream (ordered after that kernel) while the next range
+    is computed; the five narrow groups follow as one grouped collective after the last range.
 
         ar = OverlappedGradAllReduce(params.grads, N, M, nchunks=8)
         with ar:                       # registers / removes the sink for this thread
@@ -92,16 +92,24 @@ class OverlappedGradAllReduce:
 
     def _sink(self, _user, first, count, stream_ptr):
         try:
+            first, count = int(first), int(count)
             with torch.cuda.stream(torch.cuda.ExternalStream(int(stream_ptr), device=self.grads.device)):
-                views = [self.grads[o:o + n] for o, n in chunk_slices(self.N, self.M, int(first), int(count))]
-                if hasattr(dist, "_coalescing_manager"):     # one grouped NCCL launch (allreduce_coalesced) for the six slices
-                    with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
-                        for t in views:
-                            dist.all_reduce(t, group=self.group)
-                    self.works.append(cm)
-                else:
-                    for t in views:
-                        self.works.append(dist.all_reduce(t, group=self.group, async_op=True))
+                sl = chunk_slices(self.N, self.M, first, count)
+                # the SH block is 3M of the 14+3M floats per Gaussian (77 % at SH degree 3): its rows go out range by
+                # range, one plain all-reduce per range; the five narrow groups follow once, whole, as one grouped launch
+                # after the last range (few large collectives instead of many small ones)
+                o, n = sl[1]
+                self.works.append(dist.all_reduce(self.grads[o:o + n], group=self.group, async_op=True))
+                if first + count >= self.N:
+                    rest = [self.grads[o:o + n] for k, (o, n) in enumerate(chunk_slices(self.N, self.M, 0, self.N)) if k != 1]
+                    if hasattr(dist, "_coalescing_manager"):
+                        with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
+                            for t in rest:
+                                dist.all_reduce(t, group=self.group)
+                        self.works.append(cm)
+                    else:
+                        for t in rest:
+                            self.works.append(dist.all_reduce(t, group=self.group, async_op=True))
         except BaseException as e:      # never let an exception cross the C frame
             self.err = e
 
