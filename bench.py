@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", default="50000,480,270")
-    ap.add_argument("--ar-chunks", type=int, default=8, help="Gaussian-range chunks of the overlapped all-reduce")
+    ap.add_argument("--ar-chunks", type=int, default=4, help="Gaussian-range chunks of the overlapped all-reduce")
     ap.add_argument("--triangles", type=int, default=500_000, help="mesh workload: triangle count")
     return ap.parse_args()
 

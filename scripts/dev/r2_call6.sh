@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 echo "=== A/B default"; timeout 300 python scripts/dev/r2_ab.py --skip-r1 2>&1 | tail -1
-for v in "GS_B200_BWD_VOTE=0" "GS_B200_FWD_STAGES=2" "GS_B200_FWD_STAGES=4" "GS_B200_BWD_STAGES=3"; do
+for v in "GS_B200_BWD_VOTE=0" "GS_B200_FWD_STAGES=2" "GS_B200_FWD_STAGES=4" "GS_B200_BWD_STAGES=3" "GS_B200_STEP_OVERLAP=1" "GS_B200_STEP_OVERLAP=1 GS_B200_BWD_VOTE=0"; do
   echo "=== variant $v"; env $v timeout 200 python scripts/dev/r2_ab.py --skip-r1 2>&1 | tail -1
 done
 echo "=== trainer + mesh + parity gpu tests"; timeout 900 python -m pytest tests/test_gpu_trainer.py tests/test_gpu_mesh.py tests/test_gpu_parity.py -q -x > gpurun_out/r2f_tests.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/r2f_tests.log; cat gpurun_out/densify_timing.json
