@@ -694,7 +694,7 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
         GS_CUDA_CHECK(attr);                                                                                               \
         composite_backward_kernel<ST, SL, OC, VT><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
-    static const bool vote = env_int("GS_B200_BWD_VOTE", 1) != 0;
+    static const bool vote = env_int("GS_B200_BWD_VOTE", 0) != 0;     // per-visit warp vote around the sequential half: off (5 % dead visits cost less than the branch)
     if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
     else             { if (stages == 3) BWD(3, 8, 5); else if (occ >= 6) BWD(2, 8, 6); else if (occ == 5) BWD(2, 8, 5); else BWD(2, 8, 4); }
 #undef BWD_
