@@ -179,8 +179,11 @@ struct RingState {
     __device__ __forceinline__ void advance(int nstages) { if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1u; } }
 };
 
-// producer: ids (coalesced LDG) -> one 48 B bulk copy per record
-template <bool KEEP_IDS>
+// gather of one stage: ids (coalesced LDG), then per record either ONE 48 B bulk copy through the TMA engine (UBLKCP;
+// completion = bytes counted on the stage's mbarrier, which one expect_tx arrival arms) or, for the measured alternative
+// (GS_B200_GATHER=ldgsts), three 16 B cp.async (LDGSTS) per lane and record with one cp.async.mbarrier.arrive.noinc per
+// lane (the stage's mbarrier then expects 32 arrivals).
+template <bool KEEP_IDS, bool TMA>
 __device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ list, int n,
                                               uint32_t s_rec, uint32_t s_ids, uint32_t bar, int lane) {
     uint32_t id[BATCH / 32];
@@ -197,13 +200,33 @@ __device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs,
         }
         __syncwarp();
     }
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * REC_BYTES);
-    __syncwarp();
+    if (TMA) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * REC_BYTES);
+        __syncwarp();
 #pragma unroll
-    for (int i = 0; i < BATCH / 32; i++) {
-        const int j = i * 32 + lane;
-        if (j < n) bulk_g2s(s_rec + j * REC_BYTES, recs + id[i], REC_BYTES, bar);
+        for (int i = 0; i < BATCH / 32; i++) {
+            const int j = i * 32 + lane;
+            if (j < n) bulk_g2s(s_rec + j * REC_BYTES, recs + id[i], REC_BYTES, bar);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < BATCH / 32; i++) {
+            const int j = i * 32 + lane;
+            if (j < n) {
+                const char* src = reinterpret_cast<const char*>(recs + id[i]);
+                const uint32_t dst = s_rec + j * REC_BYTES;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(src + 32) : "memory");
+            }
+        }
+        if (KEEP_IDS) __threadfence_block();        // the ids written above must be visible to whoever sees the stage complete
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
     }
+}
+constexpr uint32_t full_count(bool tma) { return tma ? 1u : 32u; }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(n) : "memory");
 }
 
 // ---- one visit of the forward, split into a state-free front half and the sequential blend ------------------------
@@ -250,7 +273,7 @@ __device__ __forceinline__ void fwd_back(const FwdFront& f, bool liveA, bool liv
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int STAGES>
+template <int STAGES, bool TMA>
 __global__ void __launch_bounds__(NTHREADS)
 composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                          const uint32_t* __restrict__ ranges, float* __restrict__ out_color,
@@ -269,14 +292,14 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
     const int nb = (len + BATCH - 1) / BATCH;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); s_cnt[i] = 0; }
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, full_count(TMA)); s_cnt[i] = 0; }
         s_stop = 0xFFFFFFFFu;
         mbar_fence_init();
     }
     __syncthreads();
     // first fill of the ring: warp w gathers batch w (afterwards the LAST warp to finish a stage refills it)
     if (warp < STAGES && warp < nb)
-        produce_stage<false>(recs, point_list + start + warp * BATCH, min(BATCH, len - warp * BATCH), s_rec + warp * STAGE_BYTES, 0u,
+        produce_stage<false, TMA>(recs, point_list + start + warp * BATCH, min(BATCH, len - warp * BATCH), s_rec + warp * STAGE_BYTES, 0u,
                              a_full + 8 * warp, lane);
 
     const int X0 = blockIdx.x * GS_TILE + 8 * (warp & 1), Y0 = blockIdx.y * GS_TILE + 8 * (warp >> 1);
@@ -343,10 +366,10 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
             __syncwarp();
             if (nbatch < nb) {
                 if ((tot >> 8) == NMATH) {
-                    if (lane == 0) { atomicMin(&s_stop, (uint32_t)nbatch); __threadfence_block(); mbar_arrive(a_full + 8 * rs.stage); }
+                    if (lane == 0) { atomicMin(&s_stop, (uint32_t)nbatch); __threadfence_block(); mbar_arrive_n(a_full + 8 * rs.stage, full_count(TMA)); }
                 } else {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
-                    produce_stage<false>(recs, point_list + start + nbatch * BATCH, min(BATCH, len - nbatch * BATCH),
+                    produce_stage<false, TMA>(recs, point_list + start + nbatch * BATCH, min(BATCH, len - nbatch * BATCH),
                                          s_rec + rs.stage * STAGE_BYTES, 0u, a_full + 8 * rs.stage, lane);
                 }
             }
@@ -493,7 +516,7 @@ __device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
 }
 
-template <int STAGES, int SLOTS, int MINB, bool VOTE>
+template <int STAGES, int SLOTS, int MINB, bool VOTE, bool TMA>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                           const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
@@ -527,7 +550,7 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xFFFFFFFFu, wmax, o));
     if (lane == 0) s_wmax[warp] = wmax;
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, 1); s_cnt[i] = 0; }
+        for (int i = 0; i < STAGES; i++) { mbar_init(a_full + 8 * i, full_count(TMA)); s_cnt[i] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
@@ -537,7 +560,7 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     // stages are gathered from the back of the list: iteration `it` holds list positions [(nb-1-it)*BATCH, +BATCH)
     auto produce = [&](int it, uint32_t stage) {
         const int base = (nb - 1 - it) * BATCH;
-        produce_stage<true>(recs, point_list + start + base, min(BATCH, (int)nproc - base), s_rec + stage * STAGE_BYTES,
+        produce_stage<true, TMA>(recs, point_list + start + base, min(BATCH, (int)nproc - base), s_rec + stage * STAGE_BYTES,
                             s_ids + stage * BATCH * 4, a_full + 8 * stage, lane);
     };
     if (warp < STAGES && warp < nb) produce(warp, warp);       // first fill; afterwards the last warp to finish a stage refills it
@@ -632,6 +655,11 @@ constexpr size_t bwd_smem_bytes(int stages, int slots) {
            (size_t)stages * BATCH * 4 + 8 * (size_t)stages + 4 * (size_t)stages + 16;
 }
 
+bool gather_tma() {       // GS_B200_GATHER=ldgsts selects the cp.async gather (measurement alternative to the TMA bulk copies)
+    static const bool tma = []() { const char* e = getenv("GS_B200_GATHER"); return !(e && e[0] == 'l'); }();
+    return tma;
+}
+
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
@@ -663,12 +691,14 @@ int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uin
     if (use_r1()) return gs_launch_render_forward_r1(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T, s);
     dim3 grid(va.tiles_x, va.tiles_y);
     static const int stages = env_int("GS_B200_FWD_STAGES", 3);
-    if (stages == 2)
-        composite_forward_kernel<2><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+    if (!gather_tma())
+        composite_forward_kernel<3, false><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+    else if (stages == 2)
+        composite_forward_kernel<2, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
     else if (stages == 4)
-        composite_forward_kernel<4><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+        composite_forward_kernel<4, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
     else
-        composite_forward_kernel<3><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+        composite_forward_kernel<3, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -685,17 +715,18 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     static const int occ = env_int("GS_B200_BWD_OCC", 4);
 #define BWD(ST, SL, OC)                                                                                                    \
     do {                                                                                                                   \
-        if (vote) BWD_(ST, SL, OC, true); else BWD_(ST, SL, OC, false);                                                    \
+        if (vote) BWD_(ST, SL, OC, true, true); else BWD_(ST, SL, OC, false, true);                                        \
     } while (0)
-#define BWD_(ST, SL, OC, VT)                                                                                               \
+#define BWD_(ST, SL, OC, VT, TM)                                                                                             \
     do {                                                                                                                   \
-        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC, VT>,                    \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC, VT, TM>,                    \
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, SL)); \
         GS_CUDA_CHECK(attr);                                                                                               \
-        composite_backward_kernel<ST, SL, OC, VT><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+        composite_backward_kernel<ST, SL, OC, VT, TM><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
     static const bool vote = env_int("GS_B200_BWD_VOTE", 0) != 0;     // per-visit warp vote around the sequential half: off (5 % dead visits cost less than the branch)
-    if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
+    if (!gather_tma()) BWD_(2, 16, 4, false, false);
+    else if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
     else             { if (stages == 3) BWD(3, 8, 5); else if (occ >= 6) BWD(2, 8, 6); else if (occ == 5) BWD(2, 8, 5); else BWD(2, 8, 4); }
 #undef BWD_
 #undef BWD
