@@ -10,9 +10,9 @@
 cloud (1M Gaussians D0, SH degree 3, 1920x1080), gradients summed over views in place.
   N = 1 : config 1 — V = 8 views.
   N > 1 : config 2 — the 200-view ring dealt over the ranks, ceil(200/N) views per rank (25 at N = 8), ONE
-          all-reduce of the packed gradient buffer per step, issued in Gaussian-range chunks behind the step's last
-          pass (parallel.OverlappedGradAllReduce); the weak-scaling figure with 8 views per rank is measured too and
-          reported as config.weak_8_views_per_rank.
+          all-reduce of the packed gradient buffer per step, issued from inside the step (parallel.OverlappedGradAllReduce;
+          --ar-chunks > 1 cuts it into Gaussian-range chunks behind the last pass: measured, does not pay, DESIGN.md 7);
+          the weak-scaling figure with 8 views per rank is measured too and reported as config.weak_8_views_per_rank.
 metric = Msplats/s = N_gaussians * (views of all ranks) / t.
 """
 import argparse
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", default="50000,480,270")
-    ap.add_argument("--ar-chunks", type=int, default=4, help="Gaussian-range chunks of the overlapped all-reduce")
+    ap.add_argument("--ar-chunks", type=int, default=1, help="Gaussian-range chunks of the overlapped all-reduce")
     ap.add_argument("--triangles", type=int, default=500_000, help="mesh workload: triangle count")
     return ap.parse_args()
 
@@ -357,8 +357,8 @@ def run_gs(args):
               "views_per_gpu": V, "gaussians": N, "pairs_per_view": pairs_view, "pairs_per_view_after_tile_culling": pairs_proc,
               "l2": "inputs larger than L2 (236 MB parameters + views x 41 MB upstream gradients per step vs 126 MB L2); no flush needed",
               "parallelism": f"views sharded over {world} rank(s), Gaussians replicated" + (
-                  f", one all-reduce of the 248 MB packed gradient buffer per step in {args.ar_chunks} Gaussian-range chunks issued "
-                  "behind the step's last pass (NCCL, grouped launch per chunk)" if world > 1 else "")}
+                  f", one NCCL all-reduce of the 248 MB packed gradient buffer per step, issued from inside the step in "
+                  f"{args.ar_chunks} Gaussian-range chunk(s) (gs_b200_set_grad_sink)" if world > 1 else "")}
     if weak:
         config["weak_8_views_per_rank"] = weak
     line = {

@@ -165,7 +165,7 @@ class GaussianTrainer:
         per_view = torch.zeros(V, device=self.device)
         # data parallel: the all-reduce of the packed gradients is issued in Gaussian-range chunks from inside the step,
         # behind its last pass (parallel.OverlappedGradAllReduce); inactive without a process group
-        ar = parallel.OverlappedGradAllReduce(self.grads, self.N, self.M, nchunks=4, enabled=world > 1)
+        ar = parallel.OverlappedGradAllReduce(self.grads, self.N, self.M, nchunks=1, enabled=world > 1)
         ar.__enter__()
         try:
             self._run_views(views_np, W, H, ref_images, ref_masks, world, total, per_view, loss_fn)
