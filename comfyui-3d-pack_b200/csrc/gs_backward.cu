@@ -320,14 +320,24 @@ preprocess_backward_multi_kernel(const float* __restrict__ views, int V, int W, 
         const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
         float c[6], R[9], sc[3];
         cov3d_fwd(scales, rotations, nullptr, scale_modifier, idx, c, R, sc);
-        for (int v = 0; v < V; v++) {
-            const size_t o = (size_t)v * N + idx;
-            if (radii[o] <= 0) continue;
-            any_vis = true;
+        // visibility of every view first (V independent loads in flight instead of one load -> branch -> load chain per
+        // view), then the visible views in order with the NEXT view's screen-space gradients loading while the current
+        // view's chain is evaluated: the kernel was long-scoreboard bound at 16 warps / SM
+        uint32_t vis = 0;
+#pragma unroll 4
+        for (int v = 0; v < V; v++) vis |= (radii[(size_t)v * N + idx] > 0 ? 1u : 0u) << v;
+        any_vis = vis != 0;
+        float4 ng = make_float4(0.f, 0.f, 0.f, 0.f), nc = ng, nk = ng;
+        if (vis) { const SplatGrad* q = sg + (size_t)(__ffs(vis) - 1) * N + idx; ng = q->g; nc = q->c; nk = q->k; }
+        while (vis) {
+            const int v = __ffs(vis) - 1;
+            vis &= vis - 1;
+            const float4 cg = ng, cc = nc, ck = nk;
+            if (vis) { const SplatGrad* q = sg + (size_t)(__ffs(vis) - 1) * N + idx; ng = q->g; nc = q->c; nk = q->k; }
             const float* vw = s_views + v * 40;
             const float tfx = vw[38], tfy = vw[39];
             ViewB vb{vw, vw + 16, vw + 32, tfx, tfy, (float)W / (2.0f * tfx), (float)H / (2.0f * tfy), W, H, sh_degree};
-            backward_view<true>(vb, M, x, y, z, c, sg[o].g, sg[o].c, sg[o].k, s_sh + tid * rowp, s_dsh + tid * rowp, true, A);
+            backward_view<true>(vb, M, x, y, z, c, cg, cc, ck, s_sh + tid * rowp, s_dsh + tid * rowp, true, A);
         }
         if (any_vis) cov3d_bwd(A.dcv, R, sc, scale_modifier, rotations + 4 * (size_t)idx, dsc, dq);
     }

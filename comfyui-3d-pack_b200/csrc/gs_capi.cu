@@ -294,8 +294,8 @@ static int fwd_phase_a(FwdCtx& c, const gs_b200_view* view, int32_t N, int32_t M
     return 0;
 }
 
-// caller has made sure the D2H of phase A completed (stream or event sync)
-static int fwd_phase_b(FwdCtx& c) {
+// caller has made sure the D2H of phase A completed (stream or event sync).  Binning half: emit -> tile sort -> ranges.
+static int fwd_phase_b_bin(FwdCtx& c) {
     cudaStream_t s = c.s;
     const ViewArgs& va = c.va;
     gs_b200_state* state = c.state;
@@ -334,12 +334,20 @@ static int fwd_phase_b(FwdCtx& c) {
         if (gs_launch_ranges(state->tile_keys, (int64_t)P, state->ranges, s)) return 1; }
         STAGE_CHECK(c.dbg, s, "ranges");
     }
+    return 0;
+}
+// composite half of phase B (the only part of the forward that reads the colours in the records)
+static int fwd_phase_b_render(FwdCtx& c) {
+    cudaStream_t s = c.s;
+    const ViewArgs& va = c.va;
+    gs_b200_state* state = c.state;
     { StageTimer t(6, s);
     if (gs_launch_render_forward(va, c.recs, state->point_list, state->ranges, c.out_color, c.out_depth, c.out_alpha,
                                  state->n_contrib, state->final_T, s)) return 1; }
     STAGE_CHECK(c.dbg, s, "render");
     return 0;
 }
+static int fwd_phase_b(FwdCtx& c) { return fwd_phase_b_bin(c) || fwd_phase_b_render(c); }
 
 int32_t gs_b200_rasterize_forward(const gs_b200_view* view, int32_t N, int32_t M, const float* means3D,
                                   const float* shs, const float* colors_precomp, const float* opacities,
@@ -468,18 +476,19 @@ struct Slot {
 };
 void* slot_alloc_cb(void* user, int32_t tag, size_t bytes) { return ((Slot*)user)->alloc(tag, bytes); }
 
+constexpr int NSLOTS = 8;       // the device-resident step alternates between slots 0 and 1; the host-buffer step bins up to 8 views ahead
 struct StepCache {
-    Slot slot[2];
+    Slot slot[NSLOTS];
     bool init = false;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr, aux_stream = nullptr;
-    cudaEvent_t evFork = nullptr, evPB = nullptr, evD2H = nullptr, evAux = nullptr, evPre[2] = {nullptr, nullptr};
+    cudaEvent_t evFork = nullptr, evPB = nullptr, evGeom = nullptr, evColour = nullptr, evD2H = nullptr, evAux = nullptr, evPre[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> up_ready;          // per view: upstream gradient resident
     Region host_stage;                           // device copies of host inputs (step_host)
     bool busy = false;                           // a view hook must not re-enter the step entries on this thread
     Region ws_recs[2], ws_sg[2], ws_u32[2], ws_spans[2];               // per-chunk [VB][N] arrays of the multi-view step
     int ensure_init() {
         if (init) return 0;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < NSLOTS; i++) {
             GS_CUDA_CHECK(cudaStreamCreateWithFlags(&slot[i].stream, cudaStreamNonBlocking));
             GS_CUDA_CHECK(cudaEventCreateWithFlags(&slot[i].evA, cudaEventDisableTiming));
             GS_CUDA_CHECK(cudaEventCreateWithFlags(&slot[i].evDone, cudaEventDisableTiming));
@@ -493,6 +502,8 @@ struct StepCache {
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evD2H, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming));
         GS_CUDA_CHECK(cudaEventCreateWithFlags(&evPB, cudaEventDisableTiming));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evGeom, cudaEventDisableTiming));
+        GS_CUDA_CHECK(cudaEventCreateWithFlags(&evColour, cudaEventDisableTiming));
         init = true;
         return 0;
     }
@@ -529,7 +540,12 @@ struct GradSink { void (*fn)(void* ctx, int first, int count, cudaStream_t user)
 // view hook (optional): called on the host after view v's forward has been enqueued on its slot stream and before
 // its backward is; the callee enqueues, on that stream, whatever turns images[v] into dL_dout[v] (the loss).
 // forward_only: no backward at all (render entry).  radii_out (optional): [V][N] per-view radii.
-struct StepOpts { gs_b200_view_hook hook = nullptr; void* hook_user = nullptr; bool forward_only = false; int32_t* radii_out = nullptr; };
+// shs_ready (optional, host-buffer step): the SH block is still being uploaded when the step starts -- `user` is ordered
+// after the geometry parameters only.  Projection, depth sort and binning of every view run first (colour-free), the
+// colours are filled in when the event fires, then the composites follow.  Needs one slot per view: V <= NSLOTS, else
+// the step simply waits for the event first.
+struct StepOpts { gs_b200_view_hook hook = nullptr; void* hook_user = nullptr; bool forward_only = false; int32_t* radii_out = nullptr;
+                  cudaEvent_t shs_ready = nullptr; };
 
 int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const float* views_host,
               const float* views_dev, int N, int M, const PackedPtrs& par, const float* dL_dout_dev,
@@ -567,6 +583,10 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
     const int VB = (V + nchunks - 1) / nchunks;
     const size_t nvb = (size_t)VB * N;
     const bool tight = g_tile_culling.load() >= 1;
+    const bool late = O.shs_ready && nchunks == 1 && V <= NSLOTS && par.shs && !par.colors;
+    if (O.shs_ready && !late) GS_CUDA_CHECK(cudaStreamWaitEvent(user, O.shs_ready, 0));
+    const int nslots_used = late ? V : 2;
+    auto slot_of = [&](int j) { return late ? j : (j & 1); };
     struct WS { SplatRec* recs; SplatGrad* sg; int32_t* radii; uint32_t *tiles, *dkeys, *ids, *minkeys; uint4* spans; } ws[2];
     const int nsets = nchunks > 1 ? 2 : 1;
     for (int i = 0; i < nsets; i++) {
@@ -590,14 +610,14 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
         { StageTimer t(0, aux);
         if (gs_launch_preprocess_multi(views_dev + (size_t)v0 * 40, nv, W, H, sh_degree, scale_modifier, N, M, par.means,
                                        par.shs, par.colors, par.opac, par.scales, par.rots, w.recs, w.radii, w.tiles, w.dkeys, w.ids,
-                                       w.minkeys, w.spans, aux)) return 1; }
+                                       w.minkeys, w.spans, aux, late ? 1 : 0)) return 1; }
         GS_CUDA_CHECK(cudaEventRecord(C.evPre[k & 1], aux));
         return 0;
     };
 
-    gs_b200_state st[2];
-    gs_b200_view view[2];
-    std::unique_ptr<FwdCtx> ctx[2];                 // released on every exit path
+    gs_b200_state st[NSLOTS];
+    gs_b200_view view[NSLOTS];
+    std::unique_ptr<FwdCtx> ctx[NSLOTS];            // released on every exit path
     int64_t rendered = 0;
     int rc = enqueue_pre(0);
 
@@ -605,54 +625,81 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
         const int v0 = k * VB, nv = std::min(VB, V - v0);
         const WS& w = ws[k & (nsets - 1)];
         // the slot streams continue after this chunk's preprocess ...
-        for (int i = 0; i < 2; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evPre[k & 1], 0));
+        for (int i = 0; i < nslots_used; i++) GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[i].stream, C.evPre[k & 1], 0));
         // ... while the next chunk's preprocess already runs beside them
         if (k + 1 < nchunks && (rc = enqueue_pre(k + 1))) break;
 
         auto launch_a = [&](int j) -> int {          // j: view index inside the chunk
-            Slot& S = C.slot[j & 1];
+            const int q = slot_of(j);
+            Slot& S = C.slot[q];
             S.begin_call();
             if (!images_dev && Slot::ensure(S.image, 5 * npix * 4, S.stream)) return 1;
             const int v = v0 + j;
             const float* vh = views_host + (size_t)v * 40;
             const float* vd = views_dev + (size_t)v * 40;
-            gs_b200_view& vw = view[j & 1];
+            gs_b200_view& vw = view[q];
             vw.image_height = H; vw.image_width = W; vw.tanfovx = vh[38]; vw.tanfovy = vh[39];
             vw.bg = vd + 35; vw.scale_modifier = scale_modifier; vw.viewmatrix = vd; vw.projmatrix = vd + 16;
             vw.sh_degree = sh_degree; vw.campos = vd + 32; vw.prefiltered = 0; vw.debug = 0;
             float* img = images_dev ? images_dev + (size_t)v * 5 * npix : (float*)S.image.p;
-            ctx[j & 1].reset(new FwdCtx(slot_alloc_cb, &S, S.stream));
+            ctx[q].reset(new FwdCtx(slot_alloc_cb, &S, S.stream));
             const size_t o = (size_t)j * N;
             PreView pre{w.recs + o, w.tiles + o, w.dkeys + o, w.ids + o, w.minkeys + 2 * j, w.spans ? w.spans + o : nullptr};
-            if (fwd_phase_a(*ctx[j & 1], &vw, N, M, par.means, par.shs, par.colors, par.opac, par.scales, par.rots, nullptr,
-                            img, img + 3 * npix, img + 4 * npix, w.radii + o, &st[j & 1], S.host_total, &pre)) return 1;
+            if (fwd_phase_a(*ctx[q], &vw, N, M, par.means, par.shs, par.colors, par.opac, par.scales, par.rots, nullptr,
+                            img, img + 3 * npix, img + 4 * npix, w.radii + o, &st[q], S.host_total, &pre)) return 1;
             GS_CUDA_CHECK(cudaEventRecord(S.evA, S.stream));
             return S.failed ? 1 : 0;
         };
 
-        rc = launch_a(0);
-        for (int j = 0; j < nv && !rc; j++) {
-            Slot& S = C.slot[j & 1];
-            if (j + 1 < nv) { rc = launch_a(j + 1); if (rc) break; }
-            GS_CUDA_CHECK(cudaEventSynchronize(S.evA));
-            if ((rc = fwd_phase_b(*ctx[j & 1]))) break;
-            rendered += st[j & 1].num_rendered;
+        // after view j's forward has been enqueued: loss hook, upstream-gradient wait, composite backward
+        auto finish_view = [&](int j) -> int {
+            const int q = slot_of(j);
+            Slot& S = C.slot[q];
             const int v = v0 + j;
-            if (O.forward_only) { if (S.failed) { rc = 1; break; } continue; }
-            if (O.hook && O.hook(O.hook_user, v, (void*)S.stream) != 0) { gs_set_error("step: view hook failed at view %d", v); rc = 1; break; }
+            if (O.forward_only) return S.failed ? 1 : 0;
+            if (O.hook && O.hook(O.hook_user, v, (void*)S.stream) != 0) { gs_set_error("step: view hook failed at view %d", v); return 1; }
             const float* up = dL_dout_dev + (size_t)v * 5 * npix;
             if (up_ready) GS_CUDA_CHECK(cudaStreamWaitEvent(S.stream, up_ready[v], 0));
-            if (st[j & 1].num_rendered > 0) {
+            if (st[q].num_rendered > 0) {
                 StageTimer t(7, S.stream);
-                if ((rc = gs_launch_render_backward(ctx[j & 1]->va, (const SplatRec*)st[j & 1].geom, st[j & 1].point_list,
-                                                    st[j & 1].ranges, st[j & 1].n_contrib, st[j & 1].final_T, up,
-                                                    up + 3 * npix, up + 4 * npix, w.sg + (size_t)j * N, S.stream))) break;
+                if (gs_launch_render_backward(ctx[q]->va, (const SplatRec*)st[q].geom, st[q].point_list, st[q].ranges, st[q].n_contrib,
+                                              st[q].final_T, up, up + 3 * npix, up + 4 * npix, w.sg + (size_t)j * N, S.stream)) return 1;
             }
-            if (S.failed) { rc = 1; break; }
+            return S.failed ? 1 : 0;
+        };
+        if (late) {
+            // every view's depth sort and binning first (one slot per view, no colour needed) ...
+            for (int j = 0; j < nv && !rc; j++) rc = launch_a(j);
+            for (int j = 0; j < nv && !rc; j++) {
+                GS_CUDA_CHECK(cudaEventSynchronize(C.slot[j].evA));
+                if ((rc = fwd_phase_b_bin(*ctx[j]))) break;
+                rendered += st[j].num_rendered;
+            }
+            // ... the colours as soon as the SH block has arrived, then the composites
+            if (!rc) {
+                GS_CUDA_CHECK(cudaStreamWaitEvent(aux, O.shs_ready, 0));
+                rc = gs_launch_sh_colour_multi(views_dev + (size_t)v0 * 40, nv, sh_degree, N, M, par.means, par.shs, w.radii, w.recs, aux);
+                if (!rc) GS_CUDA_CHECK(cudaEventRecord(C.evColour, aux));
+            }
+            for (int j = 0; j < nv && !rc; j++) {
+                GS_CUDA_CHECK(cudaStreamWaitEvent(C.slot[j].stream, C.evColour, 0));
+                if ((rc = fwd_phase_b_render(*ctx[j]))) break;
+                rc = finish_view(j);
+            }
+        } else {
+            rc = launch_a(0);
+            for (int j = 0; j < nv && !rc; j++) {
+                Slot& S = C.slot[j & 1];
+                if (j + 1 < nv) { rc = launch_a(j + 1); if (rc) break; }
+                GS_CUDA_CHECK(cudaEventSynchronize(S.evA));
+                if ((rc = fwd_phase_b(*ctx[j & 1]))) break;
+                rendered += st[j & 1].num_rendered;
+                rc = finish_view(j);
+            }
         }
-        for (int i = 0; i < 2; i++) ctx[i].reset();
+        for (int i = 0; i < NSLOTS; i++) ctx[i].reset();
         // the aux stream picks up after this chunk's views (batched backward, radii copy, workspace hand-over)
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < nslots_used; i++) {
             cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
             cudaStreamWaitEvent(aux, C.slot[i].evDone, 0);
         }
@@ -673,7 +720,7 @@ int step_core(int V, int H, int W, int sh_degree, float scale_modifier, const fl
         }
     }
     // join: the caller's stream continues after the aux stream (which has waited for both slot streams)
-    for (int i = 0; i < 2; i++) {          // (on an error path the slots may not have been joined into aux yet)
+    for (int i = 0; i < nslots_used; i++) {          // (on an error path the slots may not have been joined into aux yet)
         cudaEventRecord(C.slot[i].evDone, C.slot[i].stream);
         cudaStreamWaitEvent(aux, C.slot[i].evDone, 0);
     }
@@ -709,8 +756,10 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     while ((int)C.up_ready.size() < V) {
         cudaEvent_t e; GS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); C.up_ready.push_back(e);
     }
-    // H2D order on the copy stream: parameters FIRST (compute cannot start without them), then the upstream
-    // gradients view by view (needed only at each view's backward), so they stream in behind the compute.
+    // H2D order on the copy stream: geometry parameters FIRST (projection, sorting and binning need nothing else), then
+    // the SH block (192 of the 236 B per Gaussian at degree 3; only the colours and the backward need it -- step_core
+    // bins every view while it is on its way, StepOpts::shs_ready), then the upstream gradients view by view (needed only
+    // at each view's backward), so they stream in behind the compute.  GS_B200_HOST_LATE_SH=0: wait for everything first.
     GS_CUDA_CHECK(cudaEventRecord(C.evFork, s));
     GS_CUDA_CHECK(cudaStreamWaitEvent(C.copy_stream, C.evFork, 0));
     GS_CUDA_CHECK(cudaMemcpyAsync(d_views, views_host, (size_t)V * 160, cudaMemcpyHostToDevice, C.copy_stream));
@@ -718,6 +767,7 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     GS_CUDA_CHECK(cudaMemcpyAsync(par.opac, opacities_host, (size_t)N * 4, cudaMemcpyHostToDevice, C.copy_stream));
     GS_CUDA_CHECK(cudaMemcpyAsync(par.scales, scales_host, (size_t)N * 12, cudaMemcpyHostToDevice, C.copy_stream));
     GS_CUDA_CHECK(cudaMemcpyAsync(par.rots, rotations_host, (size_t)N * 16, cudaMemcpyHostToDevice, C.copy_stream));
+    GS_CUDA_CHECK(cudaEventRecord(C.evGeom, C.copy_stream));
     GS_CUDA_CHECK(cudaMemcpyAsync(par.shs, shs_host, (size_t)N * 12 * M, cudaMemcpyHostToDevice, C.copy_stream));
     GS_CUDA_CHECK(cudaEventRecord(C.evPB, C.copy_stream));
     for (int v = 0; v < V; v++) {
@@ -725,7 +775,10 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
                                       cudaMemcpyHostToDevice, C.copy_stream));
         GS_CUDA_CHECK(cudaEventRecord(C.up_ready[v], C.copy_stream));
     }
-    GS_CUDA_CHECK(cudaStreamWaitEvent(s, C.evPB, 0));
+    static const bool late_sh = []() { const char* e = getenv("GS_B200_HOST_LATE_SH"); return !(e && e[0] == '0'); }();
+    GS_CUDA_CHECK(cudaStreamWaitEvent(s, late_sh ? C.evGeom : C.evPB, 0));
+    StepOpts opts;
+    if (late_sh) opts.shs_ready = C.evPB;
     // D2H of the summed gradients is chunked over Gaussian ranges and starts as soon as a range is final
     struct SinkCtx { StepCache* C; float* host; float* dev; size_t N, M; } sctx{&C, grads_host, d_grad, (size_t)N, (size_t)M};
     GradSink sink;
@@ -746,7 +799,7 @@ int step_host_impl(int32_t V, int32_t H, int32_t W, int32_t sh_degree, float sca
     };
     // no memset of the gradient buffer: the first view chunk's preprocess-backward writes every element (accumulate = 0)
     if (step_core(V, H, W, sh_degree, scale_modifier, views_host, d_views, N, M, par, d_up, C.up_ready.data(), grd,
-                  d_img, num_rendered_out, s, &sink)) return 1;
+                  d_img, num_rendered_out, s, &sink, &opts)) return 1;
     if (grads_dev) GS_CUDA_CHECK(cudaMemcpyAsync(grads_dev, d_grad, n_grad * 4, cudaMemcpyDeviceToDevice, s));
     if (images_host) GS_CUDA_CHECK(cudaMemcpyAsync(images_host, d_img, (size_t)V * 5 * npix * 4, cudaMemcpyDeviceToHost, s));
     if (grads_host) GS_CUDA_CHECK(cudaStreamSynchronize(C.d2h_stream));
@@ -804,7 +857,8 @@ int32_t train_loss_hook(void* user, int32_t v, void* stream_) {
     TrainLossCtx* q = (TrainLossCtx*)user;
     cudaStream_t s = (cudaStream_t)stream_;
     StepCache& C = step_cache();
-    Slot* S = (s == C.slot[0].stream) ? &C.slot[0] : &C.slot[1];
+    Slot* S = &C.slot[0];
+    for (int i = 1; i < NSLOTS; i++) if (s == C.slot[i].stream) S = &C.slot[i];
     if (Slot::ensure(S->loss_ws, gs_image_loss_scratch_bytes(q->H, q->W), s)) return 1;
     const size_t npix = (size_t)q->H * q->W;
     return gs_launch_image_loss(q->H, q->W, q->images + (size_t)v * 5 * npix, q->ref + (size_t)v * 3 * npix,

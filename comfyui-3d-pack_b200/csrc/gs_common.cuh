@@ -152,7 +152,10 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
                                int M, const float* means3D, const float* shs, const float* colors_precomp,
                                const float* opacities, const float* scales, const float* rotations, SplatRec* recs,
                                int32_t* radii, uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids,
-                               uint32_t* min_keys, uint4* spans, cudaStream_t s);
+                               uint32_t* min_keys, uint4* spans, cudaStream_t s, int geom_only = 0);
+// colours of the visible (view, Gaussian) records after a geom_only pass (host-buffer step: SH block arrives late)
+int gs_launch_sh_colour_multi(const float* views_dev, int V, int sh_degree, int N, int M, const float* means3D,
+                              const float* shs, const int32_t* radii, SplatRec* recs, cudaStream_t s);
 int gs_launch_preprocess_backward_multi(const float* views_dev, int V, int W, int H, int sh_degree,
                                         float scale_modifier, int N, int M, const float* means3D, const float* shs,
                                         const float* scales, const float* rotations, const int32_t* radii,

@@ -179,10 +179,12 @@ struct RingState {
     __device__ __forceinline__ void advance(int nstages) { if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1u; } }
 };
 
-// gather of one stage: ids (coalesced LDG), then per record either ONE 48 B bulk copy through the TMA engine (UBLKCP;
-// completion = bytes counted on the stage's mbarrier, which one expect_tx arrival arms) or, for the measured alternative
-// (GS_B200_GATHER=ldgsts), three 16 B cp.async (LDGSTS) per lane and record with one cp.async.mbarrier.arrive.noinc per
-// lane (the stage's mbarrier then expects 32 arrivals).
+// gather of one stage: ids (coalesced LDG), then per record either three 16 B cp.async (LDGSTS) per lane with one
+// cp.async.mbarrier.arrive.noinc per lane (the stage's mbarrier expects 32 arrivals) -- the default -- or
+// (GS_B200_GATHER=tma) ONE 48 B bulk copy through the TMA engine (UBLKCP; completion = bytes counted on the stage's
+// mbarrier, which one expect_tx arrival arms).  Both were measured on B200: UBLKCP takes its operands from
+// uniform registers, so a per-lane gather serialises into a ~9-instruction loop per record inside the issuing warp,
+// whereas the three LDGSTS are one warp-wide instruction each -- the whole step is 7.6 % faster with LDGSTS.
 template <bool KEEP_IDS, bool TMA>
 __device__ __forceinline__ void produce_stage(const SplatRec* __restrict__ recs, const uint32_t* __restrict__ list, int n,
                                               uint32_t s_rec, uint32_t s_ids, uint32_t bar, int lane) {
@@ -655,8 +657,8 @@ constexpr size_t bwd_smem_bytes(int stages, int slots) {
            (size_t)stages * BATCH * 4 + 8 * (size_t)stages + 4 * (size_t)stages + 16;
 }
 
-bool gather_tma() {       // GS_B200_GATHER=ldgsts selects the cp.async gather (measurement alternative to the TMA bulk copies)
-    static const bool tma = []() { const char* e = getenv("GS_B200_GATHER"); return !(e && e[0] == 'l'); }();
+bool gather_tma() {       // GS_B200_GATHER=tma selects the TMA bulk-copy gather (measured slower than the cp.async default)
+    static const bool tma = []() { const char* e = getenv("GS_B200_GATHER"); return e && e[0] == 't'; }();
     return tma;
 }
 
@@ -690,15 +692,15 @@ int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uin
                              uint32_t* n_contrib, float* final_T, cudaStream_t s) {
     if (use_r1()) return gs_launch_render_forward_r1(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T, s);
     dim3 grid(va.tiles_x, va.tiles_y);
+    // ring depth: GS_B200_FWD_STAGES (2/3/4, cp.async gather); the TMA gather (GS_B200_GATHER=tma) is kept at its best
+    // measured depth for A/B runs
     static const int stages = env_int("GS_B200_FWD_STAGES", 3);
-    if (!gather_tma())
-        composite_forward_kernel<3, false><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
-    else if (stages == 2)
-        composite_forward_kernel<2, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
-    else if (stages == 4)
-        composite_forward_kernel<4, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
-    else
-        composite_forward_kernel<3, true><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T);
+#define FWD(ST, TM) composite_forward_kernel<ST, TM><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T)
+    if (gather_tma()) FWD(3, true);
+    else if (stages == 2) FWD(2, false);
+    else if (stages == 4) FWD(4, false);
+    else FWD(3, false);
+#undef FWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -710,25 +712,20 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
                               SplatGrad* sg, cudaStream_t s) {
     if (use_r1()) return gs_launch_render_backward_r1(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg, s);
     dim3 grid(va.tiles_x, va.tiles_y);
+    // Measured on B200 and no longer instantiated: 8-slot queues with 5-6 CTAs/SM (flush overhead), forced
+    // 5 CTAs/SM at 16 slots (spills), a per-visit warp vote around the sequential half (the branch costs more than the 5 %
+    // dead visits).  Left selectable: ring depth (GS_B200_BWD_STAGES 2/3) and the TMA gather (GS_B200_GATHER=tma).
     static const int stages = env_int("GS_B200_BWD_STAGES", 2);
-    static const int slots = env_int("GS_B200_BWD_SLOTS", 16);
-    static const int occ = env_int("GS_B200_BWD_OCC", 4);
-#define BWD(ST, SL, OC)                                                                                                    \
+#define BWD(ST, TM)                                                                                                        \
     do {                                                                                                                   \
-        if (vote) BWD_(ST, SL, OC, true, true); else BWD_(ST, SL, OC, false, true);                                        \
-    } while (0)
-#define BWD_(ST, SL, OC, VT, TM)                                                                                             \
-    do {                                                                                                                   \
-        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, SL, OC, VT, TM>,                    \
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, SL)); \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, 16, 4, false, TM>,              \
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, 16)); \
         GS_CUDA_CHECK(attr);                                                                                               \
-        composite_backward_kernel<ST, SL, OC, VT, TM><<<grid, NTHREADS, bwd_smem_bytes(ST, SL), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+        composite_backward_kernel<ST, 16, 4, false, TM><<<grid, NTHREADS, bwd_smem_bytes(ST, 16), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
-    static const bool vote = env_int("GS_B200_BWD_VOTE", 0) != 0;     // per-visit warp vote around the sequential half: off (5 % dead visits cost less than the branch)
-    if (!gather_tma()) BWD_(2, 16, 4, false, false);
-    else if (slots == 16) { if (stages == 3) BWD(3, 16, 4); else if (occ >= 5) BWD(2, 16, 5); else BWD(2, 16, 4); }
-    else             { if (stages == 3) BWD(3, 8, 5); else if (occ >= 6) BWD(2, 8, 6); else if (occ == 5) BWD(2, 8, 5); else BWD(2, 8, 4); }
-#undef BWD_
+    if (gather_tma()) BWD(2, true);
+    else if (stages == 3) BWD(3, false);
+    else BWD(2, false);
 #undef BWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());

@@ -44,9 +44,11 @@ __device__ __forceinline__ void sh_to_rgb(int deg, int M, const float* __restric
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k < nb) {
-            r += bas[k] * sh[3 * k + 0];
-            g += bas[k] * sh[3 * k + 1];
-            b += bas[k] * sh[3 * k + 2];
+            // explicit FMAs: this translation unit is compiled with -fmad=false for the sake of the integer outputs
+            // (radius, tile rectangle, depth key); the colour is compared to 1e-4, so the dot product may contract
+            r = fmaf(bas[k], sh[3 * k + 0], r);
+            g = fmaf(bas[k], sh[3 * k + 1], g);
+            b = fmaf(bas[k], sh[3 * k + 2], b);
         }
     }
     r = fmaxf(r + 0.5f, 0.f); g = fmaxf(g + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
@@ -195,7 +197,8 @@ __device__ __forceinline__ void project_view(const ViewK& vk, int deg, int M, fl
     dkey = __float_as_uint(tz);
     float cr, cg, cbl;
     if (col != nullptr) { cr = col[0]; cg = col[1]; cbl = col[2]; }
-    else sh_to_rgb(deg, M, sh_row, x - vk.cam[0], y - vk.cam[1], z - vk.cam[2], cr, cg, cbl);
+    else if (sh_row != nullptr) sh_to_rgb(deg, M, sh_row, x - vk.cam[0], y - vk.cam[1], z - vk.cam[2], cr, cg, cbl);
+    else { cr = 0.f; cg = 0.f; cbl = 0.f; }       // geometry-only pass: sh_colour_multi_kernel fills the colour in later
     rec.g = make_float4(px, py, tz, __int_as_float(rad_i));
     // conic pre-scaled to log2 units for the composite: a' = -0.5*log2e*A, b' = -log2e*B, c' = -0.5*log2e*C
     const float L2E = 1.4426950408889634f;
@@ -290,8 +293,8 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
         const float tfx = vw[38], tfy = vw[39];
         ViewK vk{vw, vw + 16, vw + 32, tfx, tfy, (float)W / (2.0f * tfx), (float)H / (2.0f * tfy), W, H, tiles_x, tiles_y};
         SplatRec rec; int my_radius; uint32_t tiles, dkey; uint4 sp;
-        project_view(vk, sh_degree, M, x, y, z, c, opacity, s_sh + (idx - base) * rowp, col, rec, my_radius, tiles, dkey,
-                     spans != nullptr, sp);
+        project_view(vk, sh_degree, M, x, y, z, c, opacity, shs ? s_sh + (idx - base) * rowp : nullptr, col, rec, my_radius,
+                     tiles, dkey, spans != nullptr, sp);
         if (live) {
             const size_t o = (size_t)v * N + idx;
             if (spans) spans[o] = sp;
@@ -305,6 +308,37 @@ preprocess_multi_kernel(const float* __restrict__ views, int V, int W, int H, in
     }
     __syncthreads();
     if (tid < V && s_min[tid] != 0xFFFFFFFFu) atomicMin(min_keys + 2 * tid, s_min[tid]);
+}
+
+
+// Colour of every visible (view, Gaussian) pair written into records that a geometry-only preprocess_multi pass left
+// with zero colour: the host-buffer step starts projecting, sorting and binning while the SH block (81 % of the
+// parameter bytes) is still on its way over PCIe.  Same sh_to_rgb, same operands -> the same bits as the one-pass path.
+__global__ void __launch_bounds__(PP_THREADS)
+sh_colour_multi_kernel(const float* __restrict__ views, int V, int sh_degree, int N, int M,
+                       const float* __restrict__ means3D, const float* __restrict__ shs,
+                       const int32_t* __restrict__ radii, SplatRec* __restrict__ recs) {
+    extern __shared__ __align__(16) float s_sh[];
+    __shared__ float s_cam[PP_MAXV * 3];
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PP_THREADS;
+    if (tid < V * 3) s_cam[tid] = __ldg(views + (tid / 3) * 40 + 32 + tid % 3);
+    const int row = 3 * M;
+    const int rowp = gs_rowp(row);
+    gs_stage_rows_in(s_sh, shs + (size_t)base * row, min(PP_THREADS, N - base), row, tid, PP_THREADS);
+    __syncthreads();
+    const int idx = base + tid;
+    if (idx >= N) return;
+    const float x = means3D[3 * idx + 0], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    for (int v = 0; v < V; v++) {
+        const size_t o = (size_t)v * N + idx;
+        if (radii[o] <= 0) continue;
+        float cr, cg, cb;
+        sh_to_rgb(sh_degree, M, s_sh + tid * rowp, x - s_cam[3 * v], y - s_cam[3 * v + 1], z - s_cam[3 * v + 2], cr, cg, cb);
+        float* k = reinterpret_cast<float*>(&recs[o].k);
+        *reinterpret_cast<float2*>(k) = make_float2(cr, cg);
+        k[2] = cb;
+    }
 }
 
 }  // namespace
@@ -334,10 +368,11 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
                                int M, const float* means3D, const float* shs, const float* colors_precomp,
                                const float* opacities, const float* scales, const float* rotations, SplatRec* recs,
                                int32_t* radii, uint32_t* tiles_touched, uint32_t* depth_keys, uint32_t* ids,
-                               uint32_t* min_keys, uint4* spans, cudaStream_t s) {
+                               uint32_t* min_keys, uint4* spans, cudaStream_t s, int geom_only) {
     if (N <= 0 || V <= 0) return 0;
     if (V > PP_MAXV) { gs_set_error("preprocess_multi: V=%d > %d", V, PP_MAXV); return 1; }
-    if ((shs == nullptr) == (colors_precomp == nullptr)) { gs_set_error("preprocess_multi: exactly one of shs / colors_precomp"); return 1; }
+    if (geom_only) { shs = nullptr; colors_precomp = nullptr; }      // colours follow from gs_launch_sh_colour_multi
+    else if ((shs == nullptr) == (colors_precomp == nullptr)) { gs_set_error("preprocess_multi: exactly one of shs / colors_precomp"); return 1; }
     size_t smem = shs ? (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float) : 0;
     if (smem > 48 * 1024)
         GS_CUDA_CHECK(cudaFuncSetAttribute(preprocess_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -345,6 +380,20 @@ int gs_launch_preprocess_multi(const float* views_dev, int V, int W, int H, int 
     preprocess_multi_kernel<<<blocks, PP_THREADS, smem, s>>>(views_dev, V, W, H, sh_degree, scale_modifier, N, M, means3D,
                                                              shs, colors_precomp, opacities, scales, rotations, recs, radii,
                                                              tiles_touched, depth_keys, ids, min_keys, spans);
+    gs_count_launches(1);
+    GS_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int gs_launch_sh_colour_multi(const float* views_dev, int V, int sh_degree, int N, int M, const float* means3D,
+                              const float* shs, const int32_t* radii, SplatRec* recs, cudaStream_t s) {
+    if (N <= 0 || V <= 0) return 0;
+    if (V > PP_MAXV || !shs) { gs_set_error("sh_colour_multi: bad argument"); return 1; }
+    const size_t smem = (size_t)PP_THREADS * ((3 * M) | 1) * sizeof(float);
+    if (smem > 48 * 1024)
+        GS_CUDA_CHECK(cudaFuncSetAttribute(sh_colour_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sh_colour_multi_kernel<<<(N + PP_THREADS - 1) / PP_THREADS, PP_THREADS, smem, s>>>(views_dev, V, sh_degree, N, M, means3D, shs,
+                                                                                      radii, recs);
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -230,9 +230,11 @@ class HostStep:
                 _ptr(self.means3D), _ptr(self.shs), _ptr(self.opacities), _ptr(self.scales), _ptr(self.rotations),
                 _ptr(self.dL))
 
-    def run(self):
+    def run(self, images: torch.Tensor = None):
+        """images (optional): pinned host [V,5,H,W] fp32 that receives the rendered colour | depth | alpha planes."""
         pairs = C.c_int64(0)
-        _lib.check(_lib.lib.gs_b200_step_host(*self._args(), _ptr(self.grads), None, C.byref(pairs), _stream()))
+        _lib.check(_lib.lib.gs_b200_step_host(*self._args(), _ptr(self.grads), _ptr(images) if images is not None else None,
+                                              C.byref(pairs), _stream()))
         return int(pairs.value)
 
     def run_dev_grads(self, grads_dev: torch.Tensor):

@@ -279,6 +279,30 @@ def test_multiview_step_entries_agree_with_per_view_path(dev):
     assert np.allclose(vnp[0, :16], cam.world_view_transform.reshape(-1).cpu().numpy(), atol=1e-6)
 
 
+@pytest.mark.parametrize("V", [1, 4, 9])
+def test_host_buffer_step_bins_ahead_of_the_sh_upload_and_renders_the_same_bits(dev, V):
+    """gs_b200_step_host starts projecting / sorting / binning when the geometry parameters are resident and fills the
+    colours in when the SH block lands (V <= 8; beyond that it waits for the upload): images bit-identical to the
+    device-resident step, gradients to summation order."""
+    from gs_b200 import camera, optim_step, synthetic
+    N, W, H, deg = 30000, 320, 176, 3
+    cloud = synthetic.make_cloud("D1", N, deg, seed=9, device=dev)
+    params = optim_step.PackedParams(cloud)
+    vnp = camera.orbit_views(V, W, H)
+    views = optim_step.ViewSet(vnp, W, H, deg, dev)
+    dl_cpu = torch.rand(V, 5, H, W, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    img_dev = torch.empty(V, 5, H, W, device=dev)
+    pairs = optim_step.step_device_pipelined(params, views, dl_cpu.to(dev), img_dev)
+    g_dev = params.grads.clone()
+    hs = optim_step.HostStep({k: v.cpu() for k, v in cloud.items()}, vnp, W, H, deg, dl_cpu)
+    img_host = torch.empty(V, 5, H, W).pin_memory()
+    for _ in range(3):
+        img_host.fill_(-1.0)
+        assert hs.run(images=img_host) == pairs
+        assert torch.equal(img_host, img_dev.cpu())
+        assert float((hs.grads.to(dev) - g_dev).norm() / g_dev.norm()) < 1e-5
+
+
 def test_multiview_entries_chunking_and_empty_views(dev):
     """V = 18 > 16 views (two internal chunks), one view that sees nothing (all Gaussians behind the camera): the
     pipelined, hook, train and render entries agree with the per-view C entries."""
