@@ -144,6 +144,14 @@ __device__ __forceinline__ bool quad_hit(const float4 g, const float4 c, float X
     return !(q > tau);      // NaN -> keep (conservative)
 }
 
+// index of the highest set bit (x != 0).  `31 - __clz(x)` compiles to FLO, 31 - ., xor 31 and the mask update to a shift
+// of 0x80000000, a NOT and an AND: six instructions per visit where bfind + shift + and-not do it in three.
+__device__ __forceinline__ int hibit(uint32_t x) {
+    int h;
+    asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(x));
+    return h;
+}
+
 // hit masks of one stage for this warp's quadrant: bit l of m[i] <-> record i*32 + l
 __device__ __forceinline__ void stage_masks(uint32_t s_rec, int n, int lane, float X0, float Y0, uint32_t m[BATCH / 32]) {
 #pragma unroll
@@ -272,10 +280,44 @@ __device__ __forceinline__ void fwd_back(const FwdFront& f, bool liveA, bool liv
     pyfA = stopA ? QNAN : pyfA; pyfB = stopB ? QNAN : pyfB;
 }
 
+// Variant of fwd_back for the common case "no pixel of the warp terminates at this visit": a pixel that does not take
+// the splat blends it with alpha 0 (T * (1 - 0) = T exactly, weight 0), so T and the weights need no per-pixel
+// selects; T stays >= 1e-4 for every pixel that has not terminated, hence "T (1 - alpha) < 1e-4" alone identifies a
+// terminating pixel and ONE warp vote per visit guards the fix-up (weight 0, T kept, row coordinate poisoned).
+__device__ __forceinline__ void fwd_back_sv(const FwdFront& f, bool liveA, bool liveB, uint32_t ra, uint32_t pos, float& TA,
+                                            float& TB, FwdAcc& acc, uint32_t& lastA, uint32_t& lastB,
+                                            float& pyfA, float& pyfB) {
+    const u64 ae2 = pk(liveA ? lo(f.al2) : 0.f, liveB ? hi(f.al2) : 0.f);
+    const u64 T2 = pk(TA, TB);
+    const u64 tt2 = mul2(T2, sub2(bc(1.f), ae2));            // T * (1 - alpha)
+    const u64 w2r = mul2(ae2, T2);
+    float wA = lo(w2r), wB = hi(w2r);
+    const float oTA = TA, oTB = TB;
+    TA = lo(tt2); TB = hi(tt2);
+    bool blA = liveA, blB = liveB;
+    if (__any_sync(0xFFFFFFFFu, fminf(TA, TB) < 0.0001f)) {
+        const bool stopA = TA < 0.0001f, stopB = TB < 0.0001f;
+        const float QNAN = __int_as_float(0x7fc00000);
+        wA = stopA ? 0.f : wA; wB = stopB ? 0.f : wB;
+        TA = stopA ? oTA : TA; TB = stopB ? oTB : TB;
+        pyfA = stopA ? QNAN : pyfA; pyfB = stopB ? QNAN : pyfB;
+        blA = liveA && !stopA; blB = liveB && !stopB;
+    }
+    lastA = blA ? pos : lastA; lastB = blB ? pos : lastB;
+    const u64 w2 = pk(wA, wB);
+    const float4 k = lds128(ra + 32);
+    u64 t;
+    t = fma2(bc(k.x), w2, pk(acc.c0a, acc.c0b)); acc.c0a = lo(t); acc.c0b = hi(t);
+    t = fma2(bc(k.y), w2, pk(acc.c1a, acc.c1b)); acc.c1a = lo(t); acc.c1b = hi(t);
+    t = fma2(bc(k.z), w2, pk(acc.c2a, acc.c2b)); acc.c2a = lo(t); acc.c2b = hi(t);
+    t = fma2(bc(f.gz), w2, pk(acc.da, acc.db)); acc.da = lo(t); acc.db = hi(t);
+    t = add2(pk(acc.aa, acc.ab), w2); acc.aa = lo(t); acc.ab = hi(t);
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int STAGES, bool TMA>
+template <int STAGES, bool TMA, bool STOPVOTE>
 __global__ void __launch_bounds__(NTHREADS)
 composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                          const uint32_t* __restrict__ ranges, float* __restrict__ out_color,
@@ -341,16 +383,24 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
                     const bool two = bal != 0;
                     const int j1 = two ? __ffs(bal) - 1 : j0;
                     bal &= bal - 1;
-                    const FwdFront f0 = fwd_front(rg + j0 * REC_BYTES, pxf, pyfA, pyfB);
-                    const FwdFront f1 = fwd_front(rg + j1 * REC_BYTES, pxf, pyfA, pyfB);
+                    const uint32_t ra0 = rg + j0 * REC_BYTES, ra1 = rg + j1 * REC_BYTES;
+                    const FwdFront f0 = fwd_front(ra0, pxf, pyfA, pyfB);
+                    const FwdFront f1 = fwd_front(ra1, pxf, pyfA, pyfB);
                     // (no warp vote around the blend: 96 % of the visits have a live lane, and the branch made ptxas copy
                     // the ten accumulator registers at its join)
-                    fwd_back(f0, fwd_live(lo(f0.p2), lo(f0.al2)), fwd_live(hi(f0.p2), hi(f0.al2)), rg + j0 * REC_BYTES, pos0 + j0,
+                    if (STOPVOTE) {
+                        fwd_back_sv(f0, fwd_live(lo(f0.p2), lo(f0.al2)), fwd_live(hi(f0.p2), hi(f0.al2)), ra0, pos0 + j0,
+                                    TA, TB, acc, lastA, lastB, pyfA, pyfB);
+                        fwd_back_sv(f1, two && fwd_live(lo(f1.p2), lo(f1.al2)) && (pyfA == pyfA), two && fwd_live(hi(f1.p2), hi(f1.al2)) && (pyfB == pyfB),
+                                    ra1, pos0 + j1, TA, TB, acc, lastA, lastB, pyfA, pyfB);
+                        continue;
+                    }
+                    fwd_back(f0, fwd_live(lo(f0.p2), lo(f0.al2)), fwd_live(hi(f0.p2), hi(f0.al2)), ra0, pos0 + j0,
                              TA, TB, acc, lastA, lastB, pyfA, pyfB);
                     // visit 1's front half saw the row coordinates from before visit 0: drop pixels that just terminated
                     // (`two` false: j1 == j0 and the visit is masked off as a whole)
                     fwd_back(f1, two && fwd_live(lo(f1.p2), lo(f1.al2)) && (pyfA == pyfA), two && fwd_live(hi(f1.p2), hi(f1.al2)) && (pyfB == pyfB),
-                             rg + j1 * REC_BYTES, pos0 + j1, TA, TB, acc, lastA, lastB, pyfA, pyfB);
+                             ra1, pos0 + j1, TA, TB, acc, lastA, lastB, pyfA, pyfB);
                 }
                 if (__all_sync(0xFFFFFFFFu, (pyfA != pyfA) && (pyfB != pyfB))) { warp_done = true; break; }
             }
@@ -611,10 +661,11 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                 // two visits per iteration, from the back: everything but the T / behind recurrences and the queue slot is
                 // independent between them (bwd_front), so the two instruction streams interleave
                 while (bal) {
-                    const int j0 = 31 - __clz(bal);
-                    bal &= ~(1u << j0);
+                    const int j0 = hibit(bal);
+                    const uint32_t b0 = 1u << j0;
+                    bal &= ~b0;
                     const bool two = bal != 0;
-                    const int j1 = two ? 31 - __clz(bal) : j0;
+                    const int j1 = hibit(two ? bal : b0);        // (a select on the mask, not a branch around the bfind)
                     bal &= ~(1u << j1);
                     const BwdFront f0 = bwd_front(rg + j0 * REC_BYTES, pos0 + j0, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
@@ -695,11 +746,13 @@ int gs_launch_render_forward(const ViewArgs& va, const SplatRec* recs, const uin
     // ring depth: GS_B200_FWD_STAGES (2/3/4, cp.async gather); the TMA gather (GS_B200_GATHER=tma) is kept at its best
     // measured depth for A/B runs
     static const int stages = env_int("GS_B200_FWD_STAGES", 3);
-#define FWD(ST, TM) composite_forward_kernel<ST, TM><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T)
-    if (gather_tma()) FWD(3, true);
-    else if (stages == 2) FWD(2, false);
-    else if (stages == 4) FWD(4, false);
-    else FWD(3, false);
+    static const bool stopvote = env_int("GS_B200_FWD_STOPVOTE", 1) != 0;   // one warp vote per visit instead of per-pixel termination selects
+#define FWD(ST, TM, SV) composite_forward_kernel<ST, TM, SV><<<grid, NTHREADS, 0, s>>>(va, recs, point_list, ranges, out_color, out_depth, out_alpha, n_contrib, final_T)
+    if (gather_tma()) FWD(3, true, false);
+    else if (stages == 2) FWD(2, false, false);
+    else if (stages == 4) FWD(4, false, false);
+    else if (stopvote) FWD(3, false, true);
+    else FWD(3, false, false);
 #undef FWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());
