@@ -414,7 +414,9 @@ composite_forward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const u
         tot = __shfl_sync(0xFFFFFFFFu, tot, 0);
         if ((tot & 0xFFu) == NMATH) {
             const int nbatch = b + STAGES;
-            if (lane == 0) s_cnt[rs.stage] = 0;
+            // acquire side of the hand-over (release = the fence before each warp's atomic): the other warps' reads of
+            // the stage happen before the refill below overwrites it
+            if (lane == 0) { __threadfence_block(); s_cnt[rs.stage] = 0; }
             __syncwarp();
             if (nbatch < nb) {
                 if ((tot >> 8) == NMATH) {
@@ -458,9 +460,14 @@ template <int SLOTS> struct QGeom {
 // coordinates and the per-pixel upstream gradients; the parts are then added with shfl.xor.
 template <int SLOTS>
 __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, uint32_t slot_base, int nq, int lane,
-                                         float Xc, float Yc, SplatGrad* __restrict__ sg) {
+                                         float Xc, float Yc, const uint32_t* __restrict__ tile_list,
+                                         SplatGrad* __restrict__ sg) {
     using Q = QGeom<SLOTS>;
     const int slot = lane & (SLOTS - 1), part = lane / SLOTS;
+    // the slot remembers the list position of its splat, not its id: the id comes from the tile's list here (an L2 hit
+    // issued before the sums, so its latency hides behind them) instead of an id array staged per visit by lane 0
+    const float4 si = lds128(slot_base + slot * 16);            // mean2D.x, mean2D.y, list position, opacity
+    const uint32_t gid = (slot < nq) ? __ldg(tile_list + __float_as_uint(si.z)) : 0u;
     const uint32_t qg = q_base + slot * 8 + part * SLOTS * Q::ROW, qd = qg + 32 * Q::ROW;
     const uint32_t ca = coef_base + part * SLOTS * 32;
     float M0 = 0.f, M1 = 0.f, M2 = 0.f, My = 0.f, Mxy = 0.f, Myy = 0.f;
@@ -494,8 +501,7 @@ __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, ui
 #undef XADD
     }
     if (slot < nq) {
-        const float4 si = lds128(slot_base + slot * 16);        // mean2D.x, mean2D.y, id, opacity
-        float* dst = reinterpret_cast<float*>(sg + __float_as_uint(si.z));
+        float* dst = reinterpret_cast<float*>(sg + gid);
         // pixel = centre + L, d = mean2D - pixel = u - L with u = mean2D - centre
         const float u = si.x - Xc, v = si.y - Yc, o = si.w;
         // the ten sums of the splat = the three float4 of its SplatGrad record; one red.global.add.v4.f32 per float4
@@ -562,7 +568,7 @@ __device__ __forceinline__ void bwd_back(const BwdFront& f, u64& T2, u64& behind
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(qd), "l"(dchan) : "memory");
 }
 
-__device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_t id) {
+__device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_t id /* list position */) {
     sts64(sa, f.gx, f.gy);
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 8), "r"(id) : "memory");
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
@@ -576,14 +582,13 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                           const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dalpha,
                           SplatGrad* __restrict__ sg) {
     using Q = QGeom<SLOTS>;
-    // dynamic shared memory: ring | queue | per-pixel upstream gradients | slot info | ids | barriers | counters | wmax
+    // dynamic shared memory: ring | queue | per-pixel upstream gradients | slot info | barriers | counters | wmax
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t s_rec = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t s_q = s_rec + STAGES * STAGE_BYTES;
     const uint32_t s_coef = s_q + NMATH * Q::WARP;
     const uint32_t s_slot = s_coef + NMATH * 64 * 16;
-    const uint32_t s_ids = s_slot + NMATH * SLOTS * 16;
-    const uint32_t a_full = s_ids + STAGES * BATCH * 4;
+    const uint32_t a_full = s_slot + NMATH * SLOTS * 16;
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + (a_full + 8 * STAGES - s_rec));
     volatile uint32_t* s_wmax = s_cnt + STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -607,13 +612,14 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     }
     __syncthreads();
     const uint32_t nproc = max(max(s_wmax[0], s_wmax[1]), max(s_wmax[2], s_wmax[3]));   // list positions 1..nproc were blended
+    const uint32_t* __restrict__ tile_list = point_list + start;
     if (nproc == 0) return;
     const int nb = (int)((nproc + BATCH - 1) / BATCH);
     // stages are gathered from the back of the list: iteration `it` holds list positions [(nb-1-it)*BATCH, +BATCH)
     auto produce = [&](int it, uint32_t stage) {
         const int base = (nb - 1 - it) * BATCH;
-        produce_stage<true, TMA>(recs, point_list + start + base, min(BATCH, (int)nproc - base), s_rec + stage * STAGE_BYTES,
-                            s_ids + stage * BATCH * 4, a_full + 8 * stage, lane);
+        produce_stage<false, TMA>(recs, point_list + start + base, min(BATCH, (int)nproc - base), s_rec + stage * STAGE_BYTES,
+                             0u, a_full + 8 * stage, lane);
     };
     if (warp < STAGES && warp < nb) produce(warp, warp);       // first fill; afterwards the last warp to finish a stage refills it
 
@@ -651,13 +657,12 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
         if ((uint32_t)base < wmax) {                      // otherwise the whole stage is past this warp's last contributor
             const int n = min(BATCH, (int)nproc - base);
             const uint32_t sr = s_rec + rs.stage * STAGE_BYTES;
-            const uint32_t si = s_ids + rs.stage * BATCH * 4;
             uint32_t m[BATCH / 32];
             stage_masks(sr, n, lane, X0f, Y0f, m);
 #pragma unroll
             for (int i = BATCH / 32 - 1; i >= 0; i--) {
                 uint32_t bal = m[i];
-                const uint32_t rg = sr + i * 32 * REC_BYTES, ig = si + i * 32 * 4, pos0 = (uint32_t)(base + i * 32);
+                const uint32_t rg = sr + i * 32 * REC_BYTES, pos0 = (uint32_t)(base + i * 32);
                 // two visits per iteration, from the back: everything but the T / behind recurrences and the queue slot is
                 // independent between them (bwd_front), so the two instruction streams interleave
                 while (bal) {
@@ -671,13 +676,13 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                     const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     if (!VOTE || __any_sync(0xFFFFFFFFu, f0.any)) {
                         bwd_back(f0, T2, behind, qwG + nq * 8, qwD + nq * 8);
-                        if (lane == 0) put_slot(slot_base + nq * 16, f0, ld_volatile_s32(ig + j0 * 4));
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                        if (lane == 0) put_slot(slot_base + nq * 16, f0, pos0 + j0);
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, sg); __syncwarp(); nq = 0; }
                     }
                     if (two && (!VOTE || __any_sync(0xFFFFFFFFu, f1.any))) {
                         bwd_back(f1, T2, behind, qwG + nq * 8, qwD + nq * 8);
-                        if (lane == 0) put_slot(slot_base + nq * 16, f1, ld_volatile_s32(ig + j1 * 4));
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, sg); __syncwarp(); nq = 0; }
+                        if (lane == 0) put_slot(slot_base + nq * 16, f1, pos0 + j1);
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, sg); __syncwarp(); nq = 0; }
                     }
                 }
             }
@@ -688,7 +693,7 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
         if (lane == 0) { __threadfence_block(); tot = atomicAdd(&s_cnt[rs.stage], 1u) + 1u; }
         tot = __shfl_sync(0xFFFFFFFFu, tot, 0);
         if (tot == NMATH) {
-            if (lane == 0) s_cnt[rs.stage] = 0;
+            if (lane == 0) { __threadfence_block(); s_cnt[rs.stage] = 0; }       // acquire side of the stage hand-over
             __syncwarp();
             if (it + STAGES < nb) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was read through the generic proxy
@@ -699,13 +704,13 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     }
     if (nq > 0) {
         __syncwarp();
-        flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, sg);
+        flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, tile_list, sg);
     }
 }
 
 constexpr size_t bwd_smem_bytes(int stages, int slots) {
     return (size_t)stages * STAGE_BYTES + NMATH * 64 * (size_t)(slots + 1) * 8 + NMATH * 64 * 16 + NMATH * (size_t)slots * 16 +
-           (size_t)stages * BATCH * 4 + 8 * (size_t)stages + 4 * (size_t)stages + 16;
+           8 * (size_t)stages + 4 * (size_t)stages + 16;
 }
 
 bool gather_tma() {       // GS_B200_GATHER=tma selects the TMA bulk-copy gather (measured slower than the cp.async default)

@@ -93,7 +93,7 @@ int32_t gs_b200_set_tile_culling(int32_t mode);
 int32_t gs_b200_get_tile_culling(void);
 
 /* Measurement switch (no reference counterpart): which tile-composite kernels run.  0 (default): the round-2
- * kernels (gs_composite.cu: two pixels per lane in packed f32x2, TMA-fed mbarrier ring, queued gradient phase);
+ * kernels (gs_composite.cu: two pixels per lane in packed f32x2, cp.async-fed mbarrier ring, queued gradient phase);
  * 1: the round-1 kernels (gs_render.cu), kept for A/B timing.  Results agree (images bit for bit).
  * Initial value from the environment variable GS_B200_COMPOSITE ("r1" selects 1). */
 int32_t gs_b200_debug_set_composite(int32_t mode);
@@ -173,6 +173,10 @@ int32_t gs_b200_step_device(
  *   grads_host:   [N,(3+3M+1+3+4)] packed per parameter group in the order
  *                 means3D | shs | opacities | scales | rotations  (each contiguous), then means2D [N,3]
  *   images_host:  optional V x [5,H,W] rendered (colour, depth, alpha); may be NULL
+ * Upload order: views, geometry parameters, SH block, upstream gradients view by view.  For V <= 8 the step starts
+ * as soon as the geometry is resident (projection, sorting and binning of every view need nothing else) and fills the
+ * colours into the records when the SH block has landed; images are bit-identical to gs_b200_step_device.
+ * GS_B200_HOST_LATE_SH=0 in the environment makes it wait for the whole upload first.
  */
 int32_t gs_b200_step_host(
     int32_t V, int32_t H, int32_t W, int32_t sh_degree, float scale_modifier, const float* views_host,
