@@ -461,13 +461,21 @@ template <int SLOTS> struct QGeom {
 template <int SLOTS>
 __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, uint32_t slot_base, int nq, int lane,
                                          float Xc, float Yc, const uint32_t* __restrict__ tile_list,
-                                         SplatGrad* __restrict__ sg) {
+                                         const SplatRec* __restrict__ recs, SplatGrad* __restrict__ sg) {
     using Q = QGeom<SLOTS>;
     const int slot = lane & (SLOTS - 1), part = lane / SLOTS;
-    // the slot remembers the list position of its splat, not its id: the id comes from the tile's list here (an L2 hit
-    // issued before the sums, so its latency hides behind them) instead of an id array staged per visit by lane 0
-    const float4 si = lds128(slot_base + slot * 16);            // mean2D.x, mean2D.y, list position, opacity
-    const uint32_t gid = (slot < nq) ? __ldg(tile_list + __float_as_uint(si.z)) : 0u;
+    // a slot remembers only the list position of its splat (one 4 B store per visit by lane 0): the id comes from the
+    // tile's list and mean2D / opacity from the splat's record here -- L2 hits issued before the sums, so their latency
+    // hides behind them
+    uint32_t gid = 0u;
+    float4 si = make_float4(0.f, 0.f, 0.f, 0.f);                // mean2D.x, mean2D.y, -, opacity
+    if (slot < nq) {
+        uint32_t pos;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pos) : "r"(slot_base + slot * 4));
+        gid = __ldg(tile_list + pos);
+        const float4 g = __ldg(&recs[gid].g), c = __ldg(&recs[gid].c);
+        si = make_float4(g.x, g.y, 0.f, c.w);
+    }
     const uint32_t qg = q_base + slot * 8 + part * SLOTS * Q::ROW, qd = qg + 32 * Q::ROW;
     const uint32_t ca = coef_base + part * SLOTS * 32;
     float M0 = 0.f, M1 = 0.f, M2 = 0.f, My = 0.f, Mxy = 0.f, Myy = 0.f;
@@ -524,7 +532,7 @@ __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, ui
 }
 
 // ---- one visit of the backward: recurrence-free front half, then the short sequential part ---------------------------
-struct BwdFront { u64 al2, G2, ria, sj, bgr; float gx, gy, o; bool any; };
+struct BwdFront { u64 al2, G2, ria, sj, bgr; bool any; };
 
 __device__ __forceinline__ BwdFront bwd_front(uint32_t ra, uint32_t pos, float pxf, u64 py2, uint32_t lcA, uint32_t lcB, u64 gC0,
                                               u64 gC1, u64 gC2, u64 gD, u64 gA, u64 bgT) {
@@ -552,7 +560,6 @@ __device__ __forceinline__ BwdFront bwd_front(uint32_t ra, uint32_t pos, float p
     sj = fma2(bc(k.z), gC2, sj);
     f.sj = fma2(bc(g.z), gD, sj);
     f.bgr = mul2(bgT, f.ria);                                    // (-T_final/(1-alpha)) * bg.dL_dpixel
-    f.gx = g.x; f.gy = g.y; f.o = c.w;
     return f;
 }
 
@@ -564,14 +571,10 @@ __device__ __forceinline__ void bwd_back(const BwdFront& f, u64& T2, u64& behind
     behind = fma2(f.al2, ds, behind);                            // colour behind splat j-1
     // straight-through min(0.99, .): gradient as if unclamped (App. A.1.6); w = opacity * gda is applied per slot
     const u64 gda = mul2(f.G2, dL_da);
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(qg), "l"(gda) : "memory");
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(qd), "l"(dchan) : "memory");
-}
-
-__device__ __forceinline__ void put_slot(uint32_t sa, const BwdFront& f, uint32_t id /* list position */) {
-    sts64(sa, f.gx, f.gy);
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa + 8), "r"(id) : "memory");
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 12), "f"(f.o) : "memory");
+    // (two "f" operands, not one 64-bit "l": with the packed value as a single operand ptxas copied the pair into fresh
+    // registers before every store -- four MOVs per visit)
+    sts64(qg, lo(gda), hi(gda));
+    sts64(qd, lo(dchan), hi(dchan));
 }
 
 template <int STAGES, int SLOTS, int MINB, bool VOTE, bool TMA>
@@ -588,7 +591,7 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     const uint32_t s_q = s_rec + STAGES * STAGE_BYTES;
     const uint32_t s_coef = s_q + NMATH * Q::WARP;
     const uint32_t s_slot = s_coef + NMATH * 64 * 16;
-    const uint32_t a_full = s_slot + NMATH * SLOTS * 16;
+    const uint32_t a_full = s_slot + NMATH * SLOTS * 4;
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + (a_full + 8 * STAGES - s_rec));
     volatile uint32_t* s_wmax = s_cnt + STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -636,7 +639,7 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
 
     const uint32_t q_base = s_q + warp * Q::WARP;
     const uint32_t coef_base = s_coef + warp * 64 * 16;
-    const uint32_t slot_base = s_slot + warp * SLOTS * 16;
+    const uint32_t slot_base = s_slot + warp * SLOTS * 4;
     sts128(coef_base + lane * 32, make_float4(gC0A, gC0B, gC1A, gC1B));           // (A, B) pairs per channel: the
     sts128(coef_base + lane * 32 + 16, make_float4(gC2A, gC2B, gDA, gDB));         // second phase multiplies them packed
     const uint32_t qwG = q_base + lane * Q::ROW, qwD = qwG + 32 * Q::ROW;     // this lane's rows of the two queue arrays
@@ -676,13 +679,13 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                     const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     if (!VOTE || __any_sync(0xFFFFFFFFu, f0.any)) {
                         bwd_back(f0, T2, behind, qwG + nq * 8, qwD + nq * 8);
-                        if (lane == 0) put_slot(slot_base + nq * 16, f0, pos0 + j0);
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, sg); __syncwarp(); nq = 0; }
+                        if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot_base + nq * 4), "r"(pos0 + j0) : "memory");
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, recs, sg); __syncwarp(); nq = 0; }
                     }
                     if (two && (!VOTE || __any_sync(0xFFFFFFFFu, f1.any))) {
                         bwd_back(f1, T2, behind, qwG + nq * 8, qwD + nq * 8);
-                        if (lane == 0) put_slot(slot_base + nq * 16, f1, pos0 + j1);
-                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, sg); __syncwarp(); nq = 0; }
+                        if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot_base + nq * 4), "r"(pos0 + j1) : "memory");
+                        if (++nq == SLOTS) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, SLOTS, lane, Xc, Yc, tile_list, recs, sg); __syncwarp(); nq = 0; }
                     }
                 }
             }
@@ -704,12 +707,12 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
     }
     if (nq > 0) {
         __syncwarp();
-        flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, tile_list, sg);
+        flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, tile_list, recs, sg);
     }
 }
 
 constexpr size_t bwd_smem_bytes(int stages, int slots) {
-    return (size_t)stages * STAGE_BYTES + NMATH * 64 * (size_t)(slots + 1) * 8 + NMATH * 64 * 16 + NMATH * (size_t)slots * 16 +
+    return (size_t)stages * STAGE_BYTES + NMATH * 64 * (size_t)(slots + 1) * 8 + NMATH * 64 * 16 + NMATH * (size_t)slots * 4 +
            8 * (size_t)stages + 4 * (size_t)stages + 16;
 }
 
