@@ -535,7 +535,7 @@ __device__ __noinline__ void flush_queue(uint32_t q_base, uint32_t coef_base, ui
 struct BwdFront { u64 al2, G2, ria, sj, bgr; bool any; };
 
 __device__ __forceinline__ BwdFront bwd_front(uint32_t ra, uint32_t pos, float pxf, u64 py2, uint32_t lcA, uint32_t lcB, u64 gC0,
-                                              u64 gC1, u64 gC2, u64 gD, u64 gA, u64 bgT) {
+                                              u64 gC1, u64 gC2, u64 gD, u64 gA, u64 bgT, bool on = true) {
     BwdFront f;
     const float4 g = lds128(ra), c = lds128(ra + 16), k = lds128(ra + 32);
     const float dx = g.x - pxf;
@@ -545,8 +545,8 @@ __device__ __forceinline__ BwdFront bwd_front(uint32_t ra, uint32_t pos, float p
     float GA = ex2_approx(pA), GB = ex2_approx(pB);
     const u64 a2 = mul2(bc(c.w), pk(GA, GB));
     float alA = fminf(0.99f, lo(a2)), alB = fminf(0.99f, hi(a2));
-    const bool actA = (pos < lcA) && (pA <= 0.f) && !(alA < ALPHA_MIN);
-    const bool actB = (pos < lcB) && (pB <= 0.f) && !(alB < ALPHA_MIN);
+    const bool actA = on && (pos < lcA) && (pA <= 0.f) && !(alA < ALPHA_MIN);
+    const bool actB = on && (pos < lcB) && (pB <= 0.f) && !(alB < ALPHA_MIN);
     f.any = actA || actB;
     // a pixel the splat was not blended into runs the same code with alpha = G = 0: T, behind and both outputs are then
     // unchanged / zero
@@ -577,7 +577,10 @@ __device__ __forceinline__ void bwd_back(const BwdFront& f, u64& T2, u64& behind
     sts64(qd, lo(dchan), hi(dchan));
 }
 
-template <int STAGES, int SLOTS, int MINB, bool VOTE, bool TMA>
+// PAIR: every loop iteration runs BOTH visits; when the group has an odd number of hits the second one is masked off
+// (alpha = G = 0: T, behind and the queued values are then unchanged / zero, and its queue slot is not consumed) and the
+// queue is checked once per iteration (flushed early at SLOTS - 1) -- one branch region per iteration instead of three.
+template <int STAGES, int SLOTS, int MINB, bool VOTE, bool TMA, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const uint32_t* __restrict__ point_list,
                           const uint32_t* __restrict__ ranges, const uint32_t* __restrict__ n_contrib,
@@ -669,12 +672,25 @@ composite_backward_kernel(ViewArgs va, const SplatRec* __restrict__ recs, const 
                 // two visits per iteration, from the back: everything but the T / behind recurrences and the queue slot is
                 // independent between them (bwd_front), so the two instruction streams interleave
                 while (bal) {
+                    if (PAIR && nq > SLOTS - 2) { __syncwarp(); flush_queue<SLOTS>(q_base, coef_base, slot_base, nq, lane, Xc, Yc, tile_list, recs, sg); __syncwarp(); nq = 0; }
                     const int j0 = hibit(bal);
                     const uint32_t b0 = 1u << j0;
                     bal &= ~b0;
                     const bool two = bal != 0;
                     const int j1 = hibit(two ? bal : b0);        // (a select on the mask, not a branch around the bfind)
                     bal &= ~(1u << j1);
+                    if (PAIR) {
+                        const BwdFront g0 = bwd_front(rg + j0 * REC_BYTES, pos0 + j0, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
+                        const BwdFront g1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT, two);
+                        bwd_back(g0, T2, behind, qwG + nq * 8, qwD + nq * 8);
+                        bwd_back(g1, T2, behind, qwG + nq * 8 + 8, qwD + nq * 8 + 8);
+                        if (lane == 0) {
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot_base + nq * 4), "r"(pos0 + j0) : "memory");
+                            asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(slot_base + nq * 4), "r"(pos0 + j1) : "memory");
+                        }
+                        nq += two ? 2 : 1;
+                        continue;
+                    }
                     const BwdFront f0 = bwd_front(rg + j0 * REC_BYTES, pos0 + j0, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     const BwdFront f1 = bwd_front(rg + j1 * REC_BYTES, pos0 + j1, pxf, py2, lcA, lcB, gC0, gC1, gC2, gD, gA, bgT);
                     if (!VOTE || __any_sync(0xFFFFFFFFu, f0.any)) {
@@ -777,16 +793,18 @@ int gs_launch_render_backward(const ViewArgs& va, const SplatRec* recs, const ui
     // 5 CTAs/SM at 16 slots (spills), a per-visit warp vote around the sequential half (the branch costs more than the 5 %
     // dead visits).  Left selectable: ring depth (GS_B200_BWD_STAGES 2/3) and the TMA gather (GS_B200_GATHER=tma).
     static const int stages = env_int("GS_B200_BWD_STAGES", 2);
-#define BWD(ST, TM)                                                                                                        \
+    static const bool pair = env_int("GS_B200_BWD_PAIR", 1) != 0;      // both visits of an iteration unconditional (second masked)
+#define BWD(ST, TM, PR)                                                                                                    \
     do {                                                                                                                   \
-        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, 16, 4, false, TM>,              \
+        static const cudaError_t attr = cudaFuncSetAttribute(composite_backward_kernel<ST, 16, 4, false, TM, PR>,          \
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes(ST, 16)); \
         GS_CUDA_CHECK(attr);                                                                                               \
-        composite_backward_kernel<ST, 16, 4, false, TM><<<grid, NTHREADS, bwd_smem_bytes(ST, 16), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
+        composite_backward_kernel<ST, 16, 4, false, TM, PR><<<grid, NTHREADS, bwd_smem_bytes(ST, 16), s>>>(va, recs, point_list, ranges, n_contrib, final_T, dL_dcolor, dL_ddepth, dL_dalpha, sg); \
     } while (0)
-    if (gather_tma()) BWD(2, true);
-    else if (stages == 3) BWD(3, false);
-    else BWD(2, false);
+    if (gather_tma()) BWD(2, true, false);
+    else if (stages == 3) BWD(3, false, false);
+    else if (pair) BWD(2, false, true);
+    else BWD(2, false, false);
 #undef BWD
     gs_count_launches(1);
     GS_CUDA_CHECK(cudaGetLastError());

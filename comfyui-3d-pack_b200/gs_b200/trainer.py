@@ -250,16 +250,14 @@ class GaussianTrainer:
     def _densify_and_prune_cuda(self, max_grad, min_opacity, extent, generator, normal_samples):
         p, N, dev = self.p, self.N, self.device
         with torch.cuda.device(dev):
-            work = torch.empty(8 * N, dtype=torch.int32, device=dev)
-            counts = torch.empty(5, dtype=torch.int64, device=dev)
-            scratch = torch.empty(int(_lib.lib.gs_b200_densify_scratch_bytes(N)), dtype=torch.uint8, device=dev)
+            work, counts, scratch, zbuf = self._densify_workspace()
             _lib.check(_lib.lib.gs_b200_densify_plan(N, _ptr(self.v["opacity"]), _ptr(self.v["scaling"]), _ptr(self.grad_accum), _ptr(self.denom),
                                                      float(max_grad), float(min_opacity), float(extent), float(p.percent_dense),
                                                      _ptr(work), _ptr(counts), _ptr(scratch), _stream()))
             n_keep, n_clone, n_sp, n_spk, clone_total = (int(x) for x in counts.cpu())          # the one host sync
             n_new = n_keep + n_clone + 2 * n_spk
             if normal_samples is None:
-                z = torch.empty(2 * n_sp, 3, device=dev).normal_(generator=generator) if n_sp else torch.empty(0, 3, device=dev)
+                z = zbuf[:6 * n_sp].view(2 * n_sp, 3).normal_(generator=generator)      # (n_sp <= N <= capacity)
             else:
                 z = normal_samples.to(dev).float().contiguous()
                 assert z.shape == (2 * n_sp, 3), (z.shape, n_sp)
@@ -281,6 +279,19 @@ class GaussianTrainer:
             self._cur = 1 - self._cur
             self._bind(n_new, zero=False)
         return dict(cloned=clone_total, split=n_sp, pruned=N - n_keep, n=self.N, n_before=N)
+
+    def _densify_workspace(self):
+        """Plan arrays of the densification kernels, sized for the capacity and kept with it (grow-only like the rest):
+        a densification that fits the capacity performs no device allocation at all."""
+        ws = getattr(self, "_dws", None)
+        if ws is None or ws["cap"] < self._cap:
+            cap = self._cap
+            ws = dict(cap=cap, work=torch.empty(8 * cap, dtype=torch.int32, device=self.device),
+                      counts=torch.empty(5, dtype=torch.int64, device=self.device),
+                      scratch=torch.empty(int(_lib.lib.gs_b200_densify_scratch_bytes(cap)), dtype=torch.uint8, device=self.device),
+                      z=torch.empty(6 * cap, device=self.device))               # children offsets: 2 x split parents x 3 normals
+            self._dws = ws
+        return ws["work"], ws["counts"], ws["scratch"], ws["z"]
 
     def _alloc_grow(self, n):
         """capacity growth that keeps the live parameter set (used when a densification outgrows the buffers)."""

@@ -304,6 +304,7 @@ def test_cuda_densification_reproduces_the_reference_model_fixture_and_is_fast(d
     gen = torch.Generator(device="cpu").manual_seed(0)
     acc = (torch.rand(big.N, generator=gen) * 4e-4).to(dev)
     big._alloc_grow(int(1.6 * big.N)); big._bind(big.N, zero=False)          # head room, as after the first growth
+    big._densify_workspace()                                                  # plan arrays live with the capacity
     times = []
     for it in range(3):
         n0 = big.N
