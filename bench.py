@@ -340,7 +340,7 @@ def run_gs(args):
         ms_e2e = float(ms_e.item()) / args.steps
         e2e = {"value": N * Vp * world / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e, "views_per_gpu": Vp,
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes,
-               "api": "gs_b200_step_host (pinned host buffers; upstream-gradient uploads double-buffered on a copy stream)"}
+               "api": "gs_b200_step_host (pinned host buffers; binning of every view runs while the SH block uploads, upstream gradients stream in behind the compute, gradients go back in range chunks)"}
 
     if rank != 0:
         if world > 1:
