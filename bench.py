@@ -81,11 +81,11 @@ class Clocks:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, interval_ms=20):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(gpu_index), "-lms", str(int(interval_ms))], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -252,7 +252,10 @@ def run_gs(args):
         return dict(ms_step=ms_step, value=N * v_per_rank * world / (ms_step * 1e-3) / 1e6, launches=launches,
                     pairs=state["pairs"], vnp=vnp, views=views, dl=dl, dl_cpu=dl_cpu)
 
-    clocks = Clocks(local) if rank == 0 else None      # started before warm-up so it is sampling during the timed region
+    # started before warm-up so it is sampling during the timed region.  Multi-rank steps are long (25-100 views), so the
+    # recipe's coarser polling gives as many samples per step; on the 8-GPU box the 20 ms polling is the prime suspect for
+    # a 25-view step measuring 29.9 ms (poller on) where the 8-view step right after (poller off) scaled
+    clocks = Clocks(local, 20 if world == 1 else 100) if rank == 0 else None
     main = measure(V, args.steps, max(args.warmup, 3))
     clk = clocks.stop() if clocks else None
     ms_step, value, launches = main["ms_step"], main["value"], main["launches"]
