@@ -195,3 +195,23 @@ def test_switch_axis_and_scale_matches_the_reference_sequence():
         assert np.array_equal(out["scaling"].numpy(), f["scaling"].numpy()[:, axis])
         assert np.allclose(out["rotation"].numpy(), ref_q, atol=2e-6)
         assert out["shs"] is f["shs"] and out["opacity"] is f["opacity"]
+
+
+def test_bench_harness_imports_without_a_gpu_and_the_clock_poller_degrades_gracefully():
+    """bench.py must be importable on the CPU box (the driver parses its line there), `--impl reference` and the three
+    workloads must be selectable, and the nvidia-smi poller must neither raise nor report clocks when the tool is absent
+    or prints nothing (clocks = None is what the line then carries, never a made-up figure)."""
+    import importlib
+    import shutil
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    for interval in (20, 100):
+        c = bench.Clocks(0, interval)
+        out = c.stop()
+        assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+        if shutil.which("nvidia-smi") is None:
+            assert c.p is None and out["sm_mhz"] is None and out["reasons"] == []
+    src = open(bench.__file__).read()
+    for token in ("--impl", "--workload", "--gpus", "--steps", "--warmup", '"roofline"', '"cpu_baseline"', '"e2e"', '"gpu_launches"', '"clocks"'):
+        assert token in src, token
